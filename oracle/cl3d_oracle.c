@@ -1,0 +1,307 @@
+/*
+ * oracle/cl3d_oracle.c -- CPU restatement of the reference's five native point ops.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker, never the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product path (closerlook3d_b200/) never links, imports or falls back to anything here.
+ *
+ * Each function restates, in plain C with the reference's exact fp32 arithmetic, one CUDA kernel of
+ * zeliu98/CloserLook3D  pytorch/ops/pt_custom_ops/_ext_src/src/ :
+ *
+ *   cl3d_oracle_ball_query       <- masked_ordered_ball_query_gpu.cu:11-96   (host: masked_ordered_ball_query.cpp:13-59)
+ *   cl3d_oracle_group_points     <- group_points_gpu.cu:13-33               (host: group_points.cpp:17-40)
+ *   cl3d_oracle_group_points_grad<- group_points_gpu.cu:48-69               (host: group_points.cpp:42-65)
+ *   cl3d_oracle_nearest_query    <- masked_nearest_query_gpu.cu:8-62        (host: masked_nearest_query.cpp)
+ *   cl3d_oracle_grid_subsample   <- masked_grid_subsampling_gpu.cu:11-153   (host: masked_grid_subsampling.cpp)
+ *
+ * Parity pins (the reference ships no tests / golden vectors):
+ *   - tests/test_ref_ext_gpu.py compares this file bit-for-bit with the reference's own CUDA extension
+ *     (oracle/_ref, compiled unmodified by oracle/build_ref.py) on the GPU box;
+ *   - the distance expression follows the sm_100 SASS that nvcc 12.9 emits for the reference source
+ *     (FMUL dy*dy; FFMA dx*dx+t; FFMA dz*dz+t), checked by oracle/check_ref_sass.py.
+ *
+ * Compile with -O2 -ffp-contract=off (no implicit FMA contraction; the explicit fmaf below is the only one).
+ * OpenMP (-fopenmp) parallelises over independent queries / clouds only; results do not depend on thread count.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* d2 exactly as the compiled reference computes it (masked_ordered_ball_query_gpu.cu:56-57,
+ * masked_nearest_query_gpu.cu:47-48 after nvcc's fp contraction): d = query - support;
+ * t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t). */
+static inline float ref_d2(float qx, float qy, float qz, float x, float y, float z) {
+  float dx = qx - x, dy = qy - y, dz = qz - z;
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
+  t = fmaf(dz, dz, t);
+  return t;
+}
+
+int cl3d_oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* Stable insertion sort of (key, val) pairs by key ascending: the reference sorts each query's
+ * candidate list with an in-thread thrust::sort_by_key, which in device code is the sequential
+ * *stable* merge sort (masked_ordered_ball_query_gpu.cu:77); only stability matters. */
+static void stable_sort_pairs_f(float* key, int* val, int n) {
+  for (int i = 1; i < n; ++i) {
+    float k = key[i];
+    int v = val[i];
+    int j = i - 1;
+    while (j >= 0 && key[j] > k) {
+      key[j + 1] = key[j];
+      val[j + 1] = val[j];
+      --j;
+    }
+    key[j + 1] = k;
+    val[j + 1] = v;
+  }
+}
+
+/* masked_ordered_ball_query.  query_xyz (B,M,3), support_xyz (B,N,3), masks int32 (B,M)/(B,N),
+ * outputs idx, idx_mask (B,M,K) int32.  cnt==0 (undefined behaviour in the reference: `i % cnt`,
+ * :84) is defined here as idx=0, mask=0. */
+int cl3d_oracle_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                           const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
+                           int* idx_mask) {
+  const float radius2 = radius * radius; /* :37 fp32 product */
+  const int cap = 3 * K;
+  long total = (long)B * M;
+#pragma omp parallel
+  {
+    float* dists = (float*)malloc(sizeof(float) * (size_t)(cap > 0 ? cap : 1));
+    int* tmp = (int*)malloc(sizeof(int) * (size_t)(cap > 0 ? cap : 1));
+#pragma omp for schedule(dynamic, 64)
+    for (long t = 0; t < total; ++t) {
+      int b = (int)(t / M), j = (int)(t % M);
+      const float* s = support_xyz + (size_t)b * N * 3;
+      const int* sm = support_mask + (size_t)b * N;
+      const float* q = query_xyz + ((size_t)b * M + j) * 3;
+      int* oi = idx + ((size_t)b * M + j) * K;
+      int* om = idx_mask + ((size_t)b * M + j) * K;
+      float qx = q[0], qy = q[1], qz = q[2];
+      int cnt = 0;
+      float min_dist = radius2; /* :45 */
+      int min_idx = 0;
+      for (int k = 0; k < N; ++k) {
+        if (sm[k] == 0) break; /* :49-52 valid-prefix convention */
+        float d2 = ref_d2(qx, qy, qz, s[k * 3 + 0], s[k * 3 + 1], s[k * 3 + 2]);
+        if (d2 < radius2) {    /* strict, :58 */
+          if (d2 < min_dist) { /* first strict minimum over ALL in-radius points, :59-62 */
+            min_dist = d2;
+            min_idx = k;
+          }
+          if (cnt >= cap) continue; /* :64 keep only the first 3K by index */
+          dists[cnt] = d2;
+          tmp[cnt] = k;
+          cnt++;
+        }
+      }
+      if (cnt >= cap && cnt > 0 && min_idx > tmp[cnt - 1]) { /* :72-75 */
+        tmp[cnt - 1] = min_idx;
+        dists[cnt - 1] = min_dist;
+      }
+      stable_sort_pairs_f(dists, tmp, cnt); /* :77 */
+      for (int i = 0; i < cnt && i < K; ++i) { /* :79-82 */
+        oi[i] = tmp[i];
+        om[i] = 1;
+      }
+      for (int i = cnt; i < K; ++i) { /* :83-86 cyclic padding */
+        oi[i] = cnt > 0 ? tmp[i % cnt] : 0;
+        om[i] = 0;
+      }
+      if (query_mask[(size_t)b * M + j] == 0) /* :89-93 */
+        for (int l = 0; l < K; ++l) om[l] = 0;
+    }
+    free(dists);
+    free(tmp);
+  }
+  return 0;
+}
+
+/* group_points: out[b,c,j,k] = points[b,c,idx[b,j,k]]  (group_points_gpu.cu:25-31) */
+int cl3d_oracle_group_points(const float* points, const int* idx, int B, int C, int N, int M, int K,
+                             float* out) {
+  long rows = (long)B * C;
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < rows; ++r) {
+    int b = (int)(r / C);
+    const float* p = points + (size_t)r * N;
+    const int* id = idx + (size_t)b * M * K;
+    float* o = out + (size_t)r * M * K;
+    for (long e = 0; e < (long)M * K; ++e) o[e] = p[id[e]];
+  }
+  return 0;
+}
+
+/* group_points_grad: grad_points[b,c,idx[b,j,k]] += grad_out[b,c,j,k]  (group_points_gpu.cu:60-67).
+ * The reference uses atomicAdd (order non-deterministic); here the order is (j,k) ascending. */
+int cl3d_oracle_group_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M,
+                                  int K, float* grad_points) {
+  long rows = (long)B * C;
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < rows; ++r) {
+    int b = (int)(r / C);
+    float* gp = grad_points + (size_t)r * N;
+    const int* id = idx + (size_t)b * M * K;
+    const float* go = grad_out + (size_t)r * M * K;
+    for (int n = 0; n < N; ++n) gp[n] = 0.f;
+    for (long e = 0; e < (long)M * K; ++e) gp[id[e]] += go[e];
+  }
+  return 0;
+}
+
+/* masked_nearest_query (masked_nearest_query_gpu.cu:32-60): idx (B,M), idx_mask (B,M). */
+int cl3d_oracle_nearest_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                              const int* support_mask, int B, int N, int M, int* idx, int* idx_mask) {
+  long total = (long)B * M;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (long t = 0; t < total; ++t) {
+    int b = (int)(t / M);
+    const float* s = support_xyz + (size_t)b * N * 3;
+    const int* sm = support_mask + (size_t)b * N;
+    const float* q = query_xyz + (size_t)t * 3;
+    float min_dist = 100.f; /* :37 */
+    int min_idx = -1;
+    for (int k = 0; k < N; ++k) {
+      if (sm[k] == 0) break;
+      float d2 = ref_d2(q[0], q[1], q[2], s[k * 3 + 0], s[k * 3 + 1], s[k * 3 + 2]);
+      if (d2 < min_dist) {
+        min_dist = d2;
+        min_idx = k;
+      }
+    }
+    idx[t] = min_idx;
+    idx_mask[t] = query_mask[t] == 0 ? 0 : 1;
+  }
+  return 0;
+}
+
+/* stable merge sort of (int key, int val) pairs by key (thrust::sort_by_key in device code is stable). */
+static void stable_sort_pairs_i(int* key, int* val, int n, int* kbuf, int* vbuf) {
+  for (int width = 1; width < n; width *= 2) {
+    for (int lo = 0; lo < n; lo += 2 * width) {
+      int mid = lo + width < n ? lo + width : n;
+      int hi = lo + 2 * width < n ? lo + 2 * width : n;
+      int i = lo, j = mid, o = lo;
+      while (i < mid && j < hi) {
+        if (key[j] < key[i]) { kbuf[o] = key[j]; vbuf[o++] = val[j++]; }
+        else                 { kbuf[o] = key[i]; vbuf[o++] = val[i++]; }
+      }
+      while (i < mid) { kbuf[o] = key[i]; vbuf[o++] = val[i++]; }
+      while (j < hi)  { kbuf[o] = key[j]; vbuf[o++] = val[j++]; }
+    }
+    memcpy(key, kbuf, sizeof(int) * (size_t)n);
+    memcpy(val, vbuf, sizeof(int) * (size_t)n);
+  }
+}
+
+/* masked_grid_subsampling (masked_grid_subsampling_gpu.cu:11-153): points (B,n,3), mask (B,n) ->
+ * sub_xyz (B,m,3), sub_mask (B,m).  One cloud at a time, exactly the reference's sequence. */
+int cl3d_oracle_grid_subsample(const float* points, const int* mask, int B, int n, int m, float sampleDl,
+                               float* sub_xyz, int* sub_mask) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    const float* d = points + (size_t)b * n * 3;
+    const int* mk = mask + (size_t)b * n;
+    float* sx = sub_xyz + (size_t)b * m * 3;
+    int* smk = sub_mask + (size_t)b * m;
+    int* mapidx = (int*)malloc(sizeof(int) * (size_t)n * 4);
+    int* tempidx = mapidx + n;
+    int* kbuf = mapidx + 2 * n;
+    int* vbuf = mapidx + 3 * n;
+    float* tsub = (float*)malloc(sizeof(float) * (size_t)n * 3);
+    /* bbox over ALL n rows, padding included (:31-46) */
+    float minx = d[0], miny = d[1], minz = d[2], maxx = d[0], maxy = d[1], maxz = d[2];
+    for (int i = 1; i < n; ++i) {
+      float x = d[i * 3], y = d[i * 3 + 1], z = d[i * 3 + 2];
+      if (x > maxx) maxx = x;
+      if (y > maxy) maxy = y;
+      if (z > maxz) maxz = z;
+      if (x < minx) minx = x;
+      if (y < miny) miny = y;
+      if (z < minz) minz = z;
+    }
+    float inv = 1 / sampleDl; /* :48-50: floor(min * (1/dl)) * dl */
+    float ox = floorf(minx * inv) * sampleDl;
+    float oy = floorf(miny * inv) * sampleDl;
+    float oz = floorf(minz * inv) * sampleDl;
+    int NX = (int)floorf((maxx - ox) / sampleDl) + 1;
+    int NY = (int)floorf((maxy - oy) / sampleDl) + 1;
+    int cntv = 0;
+    for (int i = 0; i < n; ++i) { /* :59-76 */
+      if (mk[i] == 0) break;
+      int iX = (int)floorf((d[i * 3 + 0] - ox) / sampleDl);
+      int iY = (int)floorf((d[i * 3 + 1] - oy) / sampleDl);
+      int iZ = (int)floorf((d[i * 3 + 2] - oz) / sampleDl);
+      mapidx[i] = iX + NX * iY + NX * NY * iZ;
+      tempidx[i] = i;
+      cntv++;
+    }
+    int end = 0;
+    if (cntv > 0) {
+      stable_sort_pairs_i(mapidx, tempidx, cntv, kbuf, vbuf); /* :77 */
+      int cur = mapidx[0], j = tempidx[0], top = 0;
+      float xs = d[j * 3], ys = d[j * 3 + 1], zs = d[j * 3 + 2], pnum = 1;
+      for (int i = 1; i < cntv; ++i) { /* :84-122 sequential barycentre accumulation */
+        j = tempidx[i];
+        if (mapidx[i] == cur) {
+          xs += d[j * 3 + 0];
+          ys += d[j * 3 + 1];
+          zs += d[j * 3 + 2];
+          pnum += 1;
+        } else {
+          tsub[top * 3 + 0] = xs / pnum;
+          tsub[top * 3 + 1] = ys / pnum;
+          tsub[top * 3 + 2] = zs / pnum;
+          top++;
+          xs = d[j * 3];
+          ys = d[j * 3 + 1];
+          zs = d[j * 3 + 2];
+          pnum = 1;
+          cur = mapidx[i];
+        }
+      }
+      tsub[top * 3 + 0] = xs / pnum;
+      tsub[top * 3 + 1] = ys / pnum;
+      tsub[top * 3 + 2] = zs / pnum;
+      top++;
+      end = top;
+      /* pseudo-shuffle (:124-135): LCG keys seeded by the first voxel id, second stable sort */
+      mapidx[0] = mapidx[0] % 256;
+      tempidx[0] = 0;
+      for (int i = 1; i < end; ++i) {
+        mapidx[i] = (17 * mapidx[i - 1] + 139) % 256;
+        tempidx[i] = i;
+      }
+      stable_sort_pairs_i(mapidx, tempidx, end, kbuf, vbuf);
+    }
+    for (int i = 0; i < end && i < m; ++i) { /* :138-144 */
+      int j = tempidx[i];
+      sx[i * 3 + 0] = tsub[j * 3 + 0];
+      sx[i * 3 + 1] = tsub[j * 3 + 1];
+      sx[i * 3 + 2] = tsub[j * 3 + 2];
+      smk[i] = 1;
+    }
+    for (int i = end; i < m; ++i) { /* :146-151 cyclic padding with true sub points */
+      int src = end > 0 ? i % end : 0;
+      sx[i * 3 + 0] = end > 0 ? sx[src * 3 + 0] : 0.f;
+      sx[i * 3 + 1] = end > 0 ? sx[src * 3 + 1] : 0.f;
+      sx[i * 3 + 2] = end > 0 ? sx[src * 3 + 2] : 0.f;
+      smk[i] = 0;
+    }
+    free(mapidx);
+    free(tsub);
+  }
+  return 0;
+}
