@@ -1,0 +1,682 @@
+// neighbors.cu -- neighbour search for the local-aggregation engine (sm_100a).
+//
+//   cl3d_ball_query    bit-exact replacement of the reference's masked_ordered_ball_query
+//                      (/root/reference/pytorch/ops/pt_custom_ops/_ext_src/src/masked_ordered_ball_query_gpu.cu:11-96)
+//   cl3d_nearest_query bit-exact replacement of masked_nearest_query (masked_nearest_query_gpu.cu:8-62)
+//   cl3d_build_csr     transposed neighbour lists for the gather-form backward kernels
+//
+// The reference scans ALL support points per query on B thread blocks.  Here the support cloud is binned
+// into a uniform grid (cell edge >= radius, counting sort, points stored as float4 {x,y,z,index} in cell
+// order so that the three x-adjacent cells of a row are ONE contiguous, coalesced range) and one warp per
+// query walks the 9 rows of its 27 neighbouring cells.  The reference's result depends on index order
+// (first 3K in-radius points by index, nearest-overwrite rule, stable sort by distance, cyclic padding);
+// that rule is reproduced on the candidate set with 64-bit keys (d2 bits << 32 | index), which order
+// exactly like the reference's stable sort because candidates are unique in index.
+#include "common.cuh"
+
+namespace cl3d {
+
+typedef unsigned long long u64;
+
+struct GridParams {
+  float ox, oy, oz, inv_h;
+  int gx, gy, gz, ncells;
+  int n_valid, pad0, pad1, pad2;
+};
+
+constexpr int kBQWarps = 8;           // warps per CTA in the query kernels
+constexpr int kCandCap = 256;         // on-chip candidate list per warp (grid path); overflow -> exact brute force
+constexpr int kBruteMaxN = 2048;      // below this the grid is not worth its extra launches
+
+__host__ __device__ inline int cell_cap_for(int N) { return N * 4 > 4096 ? N * 4 : 4096; }
+
+// ---------------------------------------------------------------------------------------------
+// grid build
+// ---------------------------------------------------------------------------------------------
+// One CTA per cloud: n_valid = first zero of the mask (the reference stops at the first mask 0,
+// masked_ordered_ball_query_gpu.cu:49-52), bounding box of the valid prefix, grid dimensions.
+__global__ void __launch_bounds__(1024) grid_params_kernel(const float* __restrict__ xyz, const int* __restrict__ mask,
+                                                           int N, float radius, int cell_cap,
+                                                           GridParams* __restrict__ params) {
+  const int b = blockIdx.x;
+  xyz += (size_t)b * N * 3;
+  mask += (size_t)b * N;
+  __shared__ int s_first;
+  __shared__ float s_red[6][32];
+  if (threadIdx.x == 0) s_first = N;
+  __syncthreads();
+  int first = N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (mask[i] == 0) { first = i; break; }
+  if (first < N) atomicMin(&s_first, first);
+  __syncthreads();
+  const int nv = s_first;
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float v = xyz[i * 3 + a];
+      mn[a] = fminf(mn[a], v);
+      mx[a] = fmaxf(mx[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_red[a][threadIdx.x >> 5] = mn[a];
+      s_red[3 + a][threadIdx.x >> 5] = mx[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int a = 0; a < 3; ++a)
+      for (int w = 1; w < nw; ++w) {
+        s_red[a][0] = fminf(s_red[a][0], s_red[a][w]);
+        s_red[3 + a][0] = fmaxf(s_red[3 + a][0], s_red[3 + a][w]);
+      }
+    GridParams p;
+    p.n_valid = nv;
+    p.pad0 = p.pad1 = p.pad2 = 0;
+    if (nv == 0) {
+      p.ox = p.oy = p.oz = 0.f;
+      p.inv_h = 1.f;
+      p.gx = p.gy = p.gz = 1;
+      p.ncells = 1;
+    } else {
+      float ex = s_red[3][0] - s_red[0][0], ey = s_red[4][0] - s_red[1][0], ez = s_red[5][0] - s_red[2][0];
+      // cell edge strictly larger than the radius: two points closer than `radius` along an axis then land
+      // in the same or adjacent cells even after fp32 rounding of the cell coordinate (< 512 per axis).
+      float h = radius * 1.001f;
+      if (!(h > 1e-20f)) h = 1e-20f;
+      int gx = 1, gy = 1, gz = 1;
+      for (int it = 0; it < 400; ++it) {  // bounded: non-finite coordinates fall back to a single cell
+        float fx = fminf(ex / h, 510.f), fy = fminf(ey / h, 510.f), fz = fminf(ez / h, 510.f);
+        int tx = (int)fx + 1, ty = (int)fy + 1, tz = (int)fz + 1;
+        if ((long long)tx * ty * tz <= (long long)cell_cap && ex / h < 511.f && ey / h < 511.f && ez / h < 511.f) {
+          gx = tx;
+          gy = ty;
+          gz = tz;
+          break;
+        }
+        h *= 1.25f;
+      }
+      p.ox = s_red[0][0];
+      p.oy = s_red[1][0];
+      p.oz = s_red[2][0];
+      p.inv_h = 1.0f / h;
+      p.gx = gx;
+      p.gy = gy;
+      p.gz = gz;
+      p.ncells = gx * gy * gz;
+    }
+    params[b] = p;
+  }
+}
+
+__device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int g) {
+  int c = (int)((x - o) * inv_h);
+  return c < 0 ? 0 : (c >= g ? g - 1 : c);
+}
+
+__global__ void zero_cells_kernel(const GridParams* __restrict__ params, int cell_cap, int* __restrict__ cell_cnt) {
+  const int b = blockIdx.y;
+  const int nc = params[b].ncells;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x)
+    cell_cnt[(size_t)b * cell_cap + i] = 0;
+}
+
+// cell id + arrival rank inside the cell (one int atomic per point)
+__global__ void cell_count_kernel(const float* __restrict__ xyz, const GridParams* __restrict__ params, int N,
+                                  int cell_cap, int* __restrict__ cell_cnt, int2* __restrict__ cell_rank) {
+  const int b = blockIdx.y;
+  const GridParams p = params[b];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_valid) return;
+  const float* q = xyz + ((size_t)b * N + i) * 3;
+  int cx = cell_coord(q[0], p.ox, p.inv_h, p.gx);
+  int cy = cell_coord(q[1], p.oy, p.inv_h, p.gy);
+  int cz = cell_coord(q[2], p.oz, p.inv_h, p.gz);
+  int cell = cx + p.gx * (cy + p.gy * cz);
+  int r = atomicAdd(&cell_cnt[(size_t)b * cell_cap + cell], 1);
+  cell_rank[(size_t)b * N + i] = make_int2(cell, r);
+}
+
+// exclusive scan of the per-cell counts of one cloud (one CTA per cloud)
+__global__ void __launch_bounds__(1024) cell_scan_kernel(const GridParams* __restrict__ params, int cell_cap,
+                                                         const int* __restrict__ cell_cnt,
+                                                         int* __restrict__ cell_start) {
+  const int b = blockIdx.x;
+  const int nc = params[b].ncells;
+  cell_cnt += (size_t)b * cell_cap;
+  cell_start += (size_t)b * (cell_cap + 1);
+  __shared__ int s_warp[32];
+  const int per = (nc + blockDim.x - 1) / blockDim.x;
+  const int lo = min((int)threadIdx.x * per, nc), hi = min(lo + per, nc);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += cell_cnt[i];
+  // block exclusive scan of `sum`
+  int v = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += t;
+    }
+    s_warp[threadIdx.x] = w;
+  }
+  __syncthreads();
+  int base = v - sum + ((threadIdx.x >> 5) > 0 ? s_warp[(threadIdx.x >> 5) - 1] : 0);
+  for (int i = lo; i < hi; ++i) {
+    cell_start[i] = base;
+    base += cell_cnt[i];
+  }
+  if (threadIdx.x == blockDim.x - 1) cell_start[nc] = base;  // last thread's running total == n_valid
+}
+
+__global__ void cell_fill_kernel(const float* __restrict__ xyz, const GridParams* __restrict__ params, int N,
+                                 int cell_cap, const int* __restrict__ cell_start,
+                                 const int2* __restrict__ cell_rank, float4* __restrict__ sorted) {
+  const int b = blockIdx.y;
+  const int nv = params[b].n_valid;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const float* q = xyz + ((size_t)b * N + i) * 3;
+  int2 cr = cell_rank[(size_t)b * N + i];
+  int pos = cell_start[(size_t)b * (cell_cap + 1) + cr.x] + cr.y;
+  sorted[(size_t)b * N + pos] = make_float4(q[0], q[1], q[2], __int_as_float(i));
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-query selection shared by the grid and brute-force paths
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 make_key(float d2, int idx) {
+  return ((u64)__float_as_uint(d2) << 32) | (unsigned)idx;  // d2 >= +0 -> bit pattern is monotone
+}
+
+// L[0..cnt) holds the reference's candidate list (any order; unique indices).  Emits the first K of the list
+// sorted by (d2, index) -- identical to the reference's stable sort of an index-ascending list
+// (masked_ordered_ball_query_gpu.cu:77) -- then the cyclic padding (:83-86) and masks (:79-93).
+__device__ __forceinline__ void emit_query(const u64* L, int cnt, int* s_sorted, int K, int qm, int* __restrict__ idx_out,
+                                           int* __restrict__ mask_out, int* __restrict__ ncount_out) {
+  const int lane = lane_id();
+  for (int i = lane; i < cnt; i += 32) {
+    const u64 my = L[i];
+    int rho = 0;
+    for (int j = 0; j < cnt; ++j) rho += (L[j] < my) ? 1 : 0;
+    if (rho < K) s_sorted[rho] = (int)(unsigned)(my & 0xffffffffu);
+  }
+  __syncwarp();
+  for (int k = lane; k < K; k += 32) {
+    int v = 0;
+    if (cnt > 0) v = s_sorted[k < cnt ? k : (k % cnt)];
+    idx_out[k] = v;
+    if (mask_out) mask_out[k] = (k < cnt && qm != 0) ? 1 : 0;
+  }
+  if (ncount_out && lane == 0) *ncount_out = qm != 0 ? (cnt < K ? cnt : K) : K;
+  __syncwarp();
+}
+
+// Exact index-order scan of the reference (warp-cooperative): first 3K in-radius points in index order,
+// global first-strict-minimum, overwrite rule (:45-75).  Returns cnt; list in L (capacity >= 3K).
+template <typename LoadXYZ>
+__device__ __forceinline__ int brute_force_collect(LoadXYZ load, int n_valid, float qx, float qy, float qz, float r2,
+                                                   int cap3k, u64* L) {
+  const int lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
+  int T = 0;
+  u64 best = ~0ull;
+  for (int base = 0; base < n_valid; base += 32) {
+    const int i = base + lane;
+    bool in = false;
+    u64 key = 0;
+    if (i < n_valid) {
+      float x, y, z;
+      load(i, x, y, z);
+      float d2 = ref_d2(qx, qy, qz, x, y, z);
+      in = d2 < r2;
+      key = make_key(d2, i);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      int pos = T + __popc(m & lt);
+      if (pos < cap3k) L[pos] = key;
+      best = key < best ? key : best;
+    }
+    T += __popc(m);
+  }
+  __syncwarp();
+  if (T >= cap3k && cap3k > 0) {
+    best = warp_min_u64(best);
+    const u64 last = L[cap3k - 1];
+    if ((unsigned)(best & 0xffffffffu) > (unsigned)(last & 0xffffffffu)) {
+      __syncwarp();
+      if (lane == 0) L[cap3k - 1] = best;
+    }
+    __syncwarp();
+    return cap3k;
+  }
+  return T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// brute-force kernel for small clouds: the cloud's xyz lives in shared memory
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
+    const float* __restrict__ query_xyz, const float* __restrict__ support_xyz, const int* __restrict__ query_mask,
+    const int* __restrict__ support_mask, int N, int M, float radius, int K, int queries_per_cta,
+    int* __restrict__ idx, int* __restrict__ idx_mask, int* __restrict__ ncount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  const int cap3k = 3 * K;
+  float* s_xyz = reinterpret_cast<float*>(smem_raw);                            // N*3 floats
+  u64* s_list = reinterpret_cast<u64*>(smem_raw + align_up((size_t)N * 12, 16));  // warps * 3K keys
+  int* s_sorted = reinterpret_cast<int*>(s_list + (size_t)kBQWarps * cap3k);      // warps * K
+  __shared__ int s_first;
+  if (threadIdx.x == 0) s_first = N;
+  __syncthreads();
+  const int* sm = support_mask + (size_t)b * N;
+  const float* sx = support_xyz + (size_t)b * N * 3;
+  int first = N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (sm[i] == 0) { first = i; break; }
+  if (first < N) atomicMin(&s_first, first);
+  for (int i = threadIdx.x; i < N * 3; i += blockDim.x) s_xyz[i] = sx[i];
+  __syncthreads();
+  const int n_valid = s_first;
+  const int warp = threadIdx.x >> 5;
+  const float r2 = __fmul_rn(radius, radius);
+  u64* L = s_list + (size_t)warp * cap3k;
+  int* srt = s_sorted + (size_t)warp * K;
+  const int q0 = blockIdx.x * queries_per_cta;
+  const int q1 = min(q0 + queries_per_cta, M);
+  for (int q = q0 + warp; q < q1; q += kBQWarps) {
+    const float* qp = query_xyz + ((size_t)b * M + q) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    int cnt = brute_force_collect(
+        [&](int i, float& x, float& y, float& z) {
+          x = s_xyz[i * 3 + 0];
+          y = s_xyz[i * 3 + 1];
+          z = s_xyz[i * 3 + 2];
+        },
+        n_valid, qx, qy, qz, r2, cap3k, L);
+    const size_t o = ((size_t)b * M + q);
+    emit_query(L, cnt, srt, K, query_mask[o], idx + o * K, idx_mask ? idx_mask + o * K : nullptr,
+               ncount ? ncount + o : nullptr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid kernel: one warp per query, 9 contiguous cell-row ranges
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBQWarps * 32) ball_query_grid_kernel(
+    const float* __restrict__ query_xyz, const float* __restrict__ support_xyz, const int* __restrict__ query_mask,
+    const GridParams* __restrict__ params, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+    int B, int N, int M, float radius, int K, int cell_cap, int* __restrict__ idx, int* __restrict__ idx_mask,
+    int* __restrict__ ncount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cap3k = 3 * K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u64* s_cand = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * kCandCap;
+  u64* s_keep = reinterpret_cast<u64*>(smem_raw) + (size_t)kBQWarps * kCandCap + (size_t)warp * cap3k;
+  int* s_sorted = reinterpret_cast<int*>(reinterpret_cast<u64*>(smem_raw) + (size_t)kBQWarps * (kCandCap + cap3k)) +
+                  (size_t)warp * K;
+  const long long gq = (long long)blockIdx.x * kBQWarps + warp;
+  if (gq >= (long long)B * M) return;
+  const int b = (int)(gq / M);
+  const GridParams p = params[b];
+  const float* qp = query_xyz + (size_t)gq * 3;
+  const float qx = qp[0], qy = qp[1], qz = qp[2];
+  const float r2 = __fmul_rn(radius, radius);
+  const unsigned lt = (1u << lane) - 1u;
+  const int* cs = cell_start + (size_t)b * (cell_cap + 1);
+  const float4* pts = sorted + (size_t)b * N;
+
+  // query cell (may lie outside the support's bounding box)
+  float fx = floorf((qx - p.ox) * p.inv_h), fy = floorf((qy - p.oy) * p.inv_h), fz = floorf((qz - p.oz) * p.inv_h);
+  fx = fminf(fmaxf(fx, -2.f), (float)p.gx + 1.f);
+  fy = fminf(fmaxf(fy, -2.f), (float)p.gy + 1.f);
+  fz = fminf(fmaxf(fz, -2.f), (float)p.gz + 1.f);
+  const int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, p.gx - 1);
+
+  int T = 0;
+  u64 best = ~0ull;
+  if (p.n_valid > 0 && x0 <= x1) {
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int z = cz + dz;
+      if (z < 0 || z >= p.gz) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int y = cy + dy;
+        if (y < 0 || y >= p.gy) continue;
+        const int row = p.gx * (y + p.gy * z);
+        const int s = cs[row + x0], e = cs[row + x1 + 1];
+        for (int base = s; base < e; base += 32) {
+          const int i = base + lane;
+          bool in = false;
+          u64 key = 0;
+          if (i < e) {
+            const float4 c = pts[i];
+            const float d2 = ref_d2(qx, qy, qz, c.x, c.y, c.z);
+            in = d2 < r2;
+            key = make_key(d2, __float_as_int(c.w));
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, in);
+          if (in) {
+            const int pos = T + __popc(m & lt);
+            if (pos < kCandCap) s_cand[pos] = key;
+            best = key < best ? key : best;
+          }
+          T += __popc(m);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  const int qm = query_mask[gq];
+  int* io = idx + (size_t)gq * K;
+  int* mo = idx_mask ? idx_mask + (size_t)gq * K : nullptr;
+  int* no = ncount ? ncount + gq : nullptr;
+  if (T > kCandCap) {
+    // neighbourhood does not fit on chip: exact index-order scan straight from global memory (rare)
+    const float* sx = support_xyz + (size_t)b * N * 3;
+    int cnt = brute_force_collect(
+        [&](int i, float& x, float& y, float& z) {
+          x = sx[i * 3 + 0];
+          y = sx[i * 3 + 1];
+          z = sx[i * 3 + 2];
+        },
+        p.n_valid, qx, qy, qz, r2, cap3k, s_keep);
+    emit_query(s_keep, cnt, s_sorted, K, qm, io, mo, no);
+    return;
+  }
+  if (T <= cap3k) {
+    emit_query(s_cand, T, s_sorted, K, qm, io, mo, no);
+    return;
+  }
+  // more than 3K candidates: the reference keeps the 3K SMALLEST INDICES (it scans in index order, :64-68),
+  // then overwrites the last kept one with the global nearest if that lies beyond it (:72-75).
+  best = warp_min_u64(best);
+  int kept = 0;  // warp-uniform running count
+  for (int base = 0; base < T; base += 32) {
+    const int i = base + lane;
+    bool keep = false;
+    u64 my = 0;
+    if (i < T) {
+      my = s_cand[i];
+      const unsigned myidx = (unsigned)(my & 0xffffffffu);
+      int r = 0;
+      for (int j = 0; j < T; ++j) r += ((unsigned)(s_cand[j] & 0xffffffffu) < myidx) ? 1 : 0;
+      keep = r < cap3k;
+      if (r == cap3k - 1 && (unsigned)(best & 0xffffffffu) > myidx) my = best;  // overwrite rule
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) s_keep[kept + __popc(m & lt)] = my;
+    kept += __popc(m);
+  }
+  __syncwarp();
+  emit_query(s_keep, cap3k, s_sorted, K, qm, io, mo, no);
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest query: thread per query, support tiles in shared memory, sequential in index order so the
+// reference's first-strict-minimum tie rule holds (masked_nearest_query_gpu.cu:37-52)
+// ---------------------------------------------------------------------------------------------
+constexpr int kNNTile = 1024;
+__global__ void __launch_bounds__(256) nearest_query_kernel(const float* __restrict__ query_xyz,
+                                                            const float* __restrict__ support_xyz,
+                                                            const int* __restrict__ query_mask,
+                                                            const int* __restrict__ support_mask, int N, int M,
+                                                            int* __restrict__ idx, int* __restrict__ idx_mask) {
+  __shared__ float s_xyz[kNNTile * 3];
+  __shared__ int s_first;
+  const int b = blockIdx.y;
+  const float* sx = support_xyz + (size_t)b * N * 3;
+  const int* sm = support_mask + (size_t)b * N;
+  if (threadIdx.x == 0) s_first = N;
+  __syncthreads();
+  int first = N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (sm[i] == 0) { first = i; break; }
+  if (first < N) atomicMin(&s_first, first);
+  __syncthreads();
+  const int n_valid = s_first;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (q < M) {
+    const float* qp = query_xyz + ((size_t)b * M + q) * 3;
+    qx = qp[0];
+    qy = qp[1];
+    qz = qp[2];
+  }
+  float min_d = 100.f;
+  int min_i = -1;
+  for (int t0 = 0; t0 < n_valid; t0 += kNNTile) {
+    const int tn = min(kNNTile, n_valid - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) s_xyz[i] = sx[(size_t)t0 * 3 + i];
+    __syncthreads();
+    if (q < M) {
+#pragma unroll 4
+      for (int i = 0; i < tn; ++i) {
+        const float d2 = ref_d2(qx, qy, qz, s_xyz[i * 3], s_xyz[i * 3 + 1], s_xyz[i * 3 + 2]);
+        if (d2 < min_d) {
+          min_d = d2;
+          min_i = t0 + i;
+        }
+      }
+    }
+  }
+  if (q < M) {
+    idx[(size_t)b * M + q] = min_i;
+    idx_mask[(size_t)b * M + q] = query_mask[(size_t)b * M + q] == 0 ? 0 : 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR ("who gathers me") build: count -> scan -> fill
+// ---------------------------------------------------------------------------------------------
+__global__ void csr_count_kernel(const int* __restrict__ idx, const int* __restrict__ ncount, int N, int M, int K,
+                                 int* __restrict__ cnt) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)M * K) return;
+  const int q = (int)(e / K), k = (int)(e % K);
+  if (k >= ncount[(size_t)b * M + q]) return;
+  atomicAdd(&cnt[(size_t)b * N + idx[((size_t)b * M + q) * K + k]], 1);
+}
+
+__global__ void __launch_bounds__(1024) csr_scan_kernel(int N, const int* __restrict__ cnt, int* __restrict__ off,
+                                                        int* __restrict__ cursor) {
+  const int b = blockIdx.x;
+  cnt += (size_t)b * N;
+  cursor += (size_t)b * N;
+  off += (size_t)b * (N + 1);
+  __shared__ int s_warp[32];
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int lo = min(threadIdx.x * per, N), hi = min(lo + per, N);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += cnt[i];
+  int v = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += t;
+    }
+    s_warp[threadIdx.x] = w;
+  }
+  __syncthreads();
+  int base = v - sum + ((threadIdx.x >> 5) > 0 ? s_warp[(threadIdx.x >> 5) - 1] : 0);
+  for (int i = lo; i < hi; ++i) {
+    off[i] = base;
+    cursor[i] = base;
+    base += cnt[i];
+  }
+  if (threadIdx.x == blockDim.x - 1) off[N] = base;
+}
+
+__global__ void csr_fill_kernel(const int* __restrict__ idx, const int* __restrict__ ncount, int N, int M, int K,
+                                int* __restrict__ cursor, int* __restrict__ ent) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)M * K) return;
+  const int q = (int)(e / K), k = (int)(e % K);
+  if (k >= ncount[(size_t)b * M + q]) return;
+  const int j = idx[((size_t)b * M + q) * K + k];
+  const int pos = atomicAdd(&cursor[(size_t)b * N + j], 1);
+  ent[(size_t)b * M * K + pos] = (int)e;
+}
+
+}  // namespace cl3d
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace cl3d;
+
+extern "C" size_t cl3d_ball_query_workspace_bytes(int B, int N, int M, int K) {
+  (void)M;
+  (void)K;
+  if (B <= 0 || N <= 0) return 256;
+  const size_t cap = (size_t)cell_cap_for(N);
+  size_t s = 0;
+  s += align_up(sizeof(GridParams) * (size_t)B, 256);
+  s += align_up(sizeof(int) * (size_t)B * cap, 256);        // cell_cnt
+  s += align_up(sizeof(int) * (size_t)B * (cap + 1), 256);  // cell_start
+  s += align_up(sizeof(int2) * (size_t)B * N, 256);         // cell id + rank
+  s += align_up(sizeof(float4) * (size_t)B * N, 256);       // cell-sorted points
+  return s;
+}
+
+extern "C" int cl3d_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                               const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
+                               int* idx_mask, int* ncount, void* workspace, size_t workspace_bytes,
+                               cl3d_stream_t stream_) {
+  return cl3d_ball_query_algo(query_xyz, support_xyz, query_mask, support_mask, B, N, M, radius, K, idx, idx_mask,
+                              ncount, workspace, workspace_bytes, CL3D_BQ_AUTO, stream_);
+}
+
+extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                                    const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
+                                    int* idx_mask, int* ncount, void* workspace, size_t workspace_bytes, int algo,
+                                    cl3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0 && K >= 1, "cl3d_ball_query: bad sizes B=%d N=%d M=%d K=%d", B, N, M, K);
+  CL3D_REQUIRE(K <= 256, "cl3d_ball_query: nsample %d > 256 unsupported", K);
+  CL3D_REQUIRE(query_xyz && support_xyz && query_mask && support_mask && idx, "cl3d_ball_query: null pointer");
+  if (B == 0 || M == 0) return CL3D_OK;
+  const int cap3k = 3 * K;
+  CL3D_REQUIRE(algo != CL3D_BQ_BRUTE || N <= 8192, "cl3d_ball_query: brute-force path limited to N <= 8192");
+  const bool brute = algo == CL3D_BQ_BRUTE || (algo == CL3D_BQ_AUTO && N <= kBruteMaxN);
+  if (brute) {
+    size_t smem = align_up((size_t)N * 12, 16) + (size_t)kBQWarps * cap3k * 8 + (size_t)kBQWarps * K * 4;
+    const int qpc = 64;  // queries per CTA (8 per warp): amortises the cloud load, keeps >= 148 CTAs at c2
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(ball_query_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    dim3 grid(ceil_div(M, qpc), B);
+    ball_query_brute_kernel<<<grid, kBQWarps * 32, smem, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
+                                                                   N, M, radius, K, qpc, idx, idx_mask, ncount);
+    return check_launch("ball_query_brute_kernel");
+  }
+  if (workspace_bytes < cl3d_ball_query_workspace_bytes(B, N, M, K) || !workspace) {
+    set_error("cl3d_ball_query: workspace too small (%zu < %zu)", workspace_bytes,
+              cl3d_ball_query_workspace_bytes(B, N, M, K));
+    return CL3D_ERR_WORKSPACE;
+  }
+  const int cap = cell_cap_for(N);
+  unsigned char* w = (unsigned char*)workspace;
+  GridParams* params = (GridParams*)w;
+  w += align_up(sizeof(GridParams) * (size_t)B, 256);
+  int* cell_cnt = (int*)w;
+  w += align_up(sizeof(int) * (size_t)B * cap, 256);
+  int* cell_start = (int*)w;
+  w += align_up(sizeof(int) * (size_t)B * (cap + 1), 256);
+  int2* cell_rank = (int2*)w;
+  w += align_up(sizeof(int2) * (size_t)B * N, 256);
+  float4* sorted = (float4*)w;
+
+  grid_params_kernel<<<B, 1024, 0, stream>>>(support_xyz, support_mask, N, radius, cap, params);
+  zero_cells_kernel<<<dim3(64, B), 256, 0, stream>>>(params, cap, cell_cnt);
+  cell_count_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_cnt, cell_rank);
+  cell_scan_kernel<<<B, 1024, 0, stream>>>(params, cap, cell_cnt, cell_start);
+  cell_fill_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_start, cell_rank,
+                                                                  sorted);
+  size_t smem = (size_t)kBQWarps * (kCandCap + cap3k) * 8 + (size_t)kBQWarps * K * 4;
+  static bool attr_set2 = false;
+  if (!attr_set2) {
+    cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set2 = true;
+  }
+  const long long total = (long long)B * M;
+  ball_query_grid_kernel<<<(unsigned)((total + kBQWarps - 1) / kBQWarps), kBQWarps * 32, smem, stream>>>(
+      query_xyz, support_xyz, query_mask, params, cell_start, sorted, B, N, M, radius, K, cap, idx, idx_mask, ncount);
+  return check_launch("ball_query_grid_kernel");
+}
+
+extern "C" int cl3d_nearest_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                                  const int* support_mask, int B, int N, int M, int* idx, int* idx_mask,
+                                  cl3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0, "cl3d_nearest_query: bad sizes");
+  CL3D_REQUIRE(query_xyz && support_xyz && query_mask && support_mask && idx && idx_mask,
+               "cl3d_nearest_query: null pointer");
+  if (B == 0 || M == 0) return CL3D_OK;
+  nearest_query_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
+                                                                      N, M, idx, idx_mask);
+  return check_launch("nearest_query_kernel");
+}
+
+extern "C" size_t cl3d_csr_workspace_bytes(int B, int N, int M, int K) {
+  (void)M;
+  (void)K;
+  return align_up(sizeof(int) * (size_t)(B > 0 ? B : 1) * (size_t)(N > 0 ? N : 1), 256) * 2;
+}
+
+extern "C" int cl3d_build_csr(const int* idx, const int* ncount, int B, int N, int M, int K, int* csr_off,
+                              int* csr_ent, void* workspace, size_t workspace_bytes, cl3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0 && K >= 1, "cl3d_build_csr: bad sizes");
+  CL3D_REQUIRE(idx && ncount && csr_off && csr_ent, "cl3d_build_csr: null pointer");
+  if (workspace_bytes < cl3d_csr_workspace_bytes(B, N, M, K) || !workspace) {
+    set_error("cl3d_build_csr: workspace too small");
+    return CL3D_ERR_WORKSPACE;
+  }
+  if (B == 0) return CL3D_OK;
+  int* cnt = (int*)workspace;
+  int* cursor = (int*)((unsigned char*)workspace + align_up(sizeof(int) * (size_t)B * N, 256));
+  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)B * N, stream);
+  const long long ents = (long long)M * K;
+  if (ents > 0) {
+    csr_count_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, N, M, K, cnt);
+  }
+  csr_scan_kernel<<<B, 1024, 0, stream>>>(N, cnt, csr_off, cursor);
+  if (ents > 0) {
+    csr_fill_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, N, M, K, cursor, csr_ent);
+  }
+  return check_launch("csr kernels");
+}
