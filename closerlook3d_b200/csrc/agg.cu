@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_fwd_kernel(const AggArgs a
         if (FAM == CL3D_FAM_PSEUDOGRID) {
           for (int kp = 0; kp < a.nkp; ++kp)
             s_h[k * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
+          for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[k * kMaxKP + kp] = 0.f;
         }
       }
       __syncwarp();
@@ -520,9 +521,10 @@ static int launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   return check_launch("agg_bwd_kernel");
 }
 
-static int pick_ci(int Cp) {
+static int pick_ci(int family, int Cp) {
   int ci = ceil_div(Cp, 32);
-  return ci > kMaxCI ? kMaxCI : ci;
+  const int cap = family == CL3D_FAM_PSEUDOGRID ? 3 : kMaxCI;  // PseudoGrid keeps nkp accumulators per channel
+  return ci > cap ? cap : ci;
 }
 
 #define DISPATCH_CI(FN, FAM, ...)                          \
@@ -615,7 +617,7 @@ extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, con
   a.inv_radius = 1.0f / radius;
   a.extent = extent;
   a.ntiles = B * ceil_div(M, kTile);
-  const int ci = pick_ci(a.Cp);
+  const int ci = pick_ci(family, a.Cp);
   const int chunk = 32 * ci < a.Cp ? 32 * ci : a.Cp;
   a.rows_per_stage = kStageBytes / (chunk * 4);
   if (a.rows_per_stage > K) a.rows_per_stage = K;
@@ -656,7 +658,7 @@ extern "C" int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const 
   a.inv_radius = 1.0f / radius;
   a.extent = extent;
   a.ntiles = B * ceil_div(N, kTile);
-  const int ci = pick_ci(a.Cp);
+  const int ci = pick_ci(family, a.Cp);
   const int chunk = 32 * ci < a.Cp ? 32 * ci : a.Cp;
   a.rows_per_stage = kStageBytes / (chunk * 4);
   if (a.rows_per_stage > 64) a.rows_per_stage = 64;

@@ -4,13 +4,6 @@ using namespace cl3d;
 #define STUB(name) { set_error(#name ": not implemented yet"); return CL3D_ERR_UNSUPPORTED; }
 extern "C" size_t cl3d_grid_subsample_workspace_bytes(int, int, int) { return 256; }
 extern "C" int cl3d_grid_subsample(const float*, const int*, int, int, int, float, float*, int*, void*, size_t, cl3d_stream_t) STUB(cl3d_grid_subsample)
-extern "C" int cl3d_agg_num_tiles(int, int) { return 0; }
-extern "C" int cl3d_agg_num_params(int, int, int, int) { return 0; }
-extern "C" int cl3d_agg_fwd(int, int, const float*, const float*, const float*, const int*, const int*, const float*, int, int, int, int, int, float, int, int, int, float, int, float*, float*, cl3d_stream_t) STUB(cl3d_agg_fwd)
-extern "C" int cl3d_agg_bwd(int, int, const float*, const float*, const float*, const float*, const int*, const int*, const int*, const float*, int, int, int, int, int, float, int, int, int, float, int, float*, float*, cl3d_stream_t) STUB(cl3d_agg_bwd)
-extern "C" int cl3d_bn_finalize(const float*, int, int, long long, float, float, int, float*, float*, float*, cl3d_stream_t) STUB(cl3d_bn_finalize)
-extern "C" int cl3d_bn_relu_fwd(const float*, const float*, const float*, const float*, int, int, int, float*, cl3d_stream_t) STUB(cl3d_bn_relu_fwd)
-extern "C" int cl3d_bn_relu_bwd(const float*, const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, float*, cl3d_stream_t) STUB(cl3d_bn_relu_bwd)
 extern "C" int cl3d_sgemm_nt(const float*, int, const float*, int, int, int, int, float*, int, cl3d_stream_t) STUB(cl3d_sgemm_nt)
 extern "C" int cl3d_pwmlp_fwd_stats(const float*, const float*, const float*, const float*, const float*, const int*, int, int, int, int, int, float, float*, float*, unsigned char*, unsigned char*, float*, cl3d_stream_t) STUB(cl3d_pwmlp_fwd_stats)
 extern "C" int cl3d_pwmlp_fwd_out(const float*, const float*, const float*, const float*, const float*, int, int, int, float*, cl3d_stream_t) STUB(cl3d_pwmlp_fwd_out)

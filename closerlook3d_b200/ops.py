@@ -111,3 +111,76 @@ def reduce_partials(partial):
     out = torch.empty(P, dtype=F32, device=partial.device)
     check(_lib.lib().cl3d_reduce_partials(ptr(partial), T, P, ptr(out), stream_ptr()), "cl3d_reduce_partials")
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# fused aggregation + out_transform
+# --------------------------------------------------------------------------------------------------
+FAM_POSPOOL_XYZ, FAM_POSPOOL_SINCOS, FAM_ADAPTIVE_DP, FAM_PSEUDOGRID = 0, 1, 2, 3
+REDUCE = {"avg": 0, "mean": 0, "sum": 1, "max": 2}
+
+
+def agg_fwd(family, reduction, feat_pm, query_xyz, support_xyz, idx, ncount, p0, p1, C, radius, normalize, shared=1,
+            nkp=0, extent=1.0, influence=0, want_bn_partial=True):
+    """-> (agg (B,C,M), bn_partial (ntiles,2,C) | None)"""
+    B, N, Cp = feat_pm.shape
+    M, K = idx.shape[1], idx.shape[2]
+    L = _lib.lib()
+    dev = feat_pm.device
+    agg = torch.empty(B, C, M, dtype=F32, device=dev)
+    partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, C, dtype=F32, device=dev) if want_bn_partial else None
+    check(L.cl3d_agg_fwd(family, reduction, ptr(feat_pm), ptr(query_xyz), ptr(support_xyz), ptr(idx), ptr(ncount),
+                         ptr(p0), ptr(p1), B, N, M, K, C, float(radius), int(normalize), int(shared), int(nkp),
+                         float(extent), int(influence), ptr(agg), ptr(partial), stream_ptr()), "cl3d_agg_fwd")
+    return agg, partial
+
+
+def agg_bwd(family, reduction, g_pm, feat_pm, query_xyz, support_xyz, ncount, csr_off, csr_ent, p0, p1, C, N, K,
+            radius, normalize, shared=1, nkp=0, extent=1.0, influence=0):
+    """-> (grad_feat (B,C,N), param_grad (P//C, C) | None)   P = 4C (adaptive: x,y,z,bias) or nkp*C"""
+    B, M, Cp = g_pm.shape
+    L = _lib.lib()
+    dev = g_pm.device
+    grad_feat = torch.empty(B, C, N, dtype=F32, device=dev)
+    P = L.cl3d_agg_num_params(family, C, shared, nkp)
+    partial = None
+    if P > 0:
+        partial = torch.empty(L.cl3d_agg_bwd_num_blocks(B, N), P, dtype=F32, device=dev)
+    check(L.cl3d_agg_bwd(family, reduction, ptr(g_pm), ptr(feat_pm), ptr(query_xyz), ptr(support_xyz), ptr(ncount),
+                         ptr(csr_off), ptr(csr_ent), ptr(p0), ptr(p1), B, N, M, K, C, float(radius), int(normalize),
+                         int(shared), int(nkp), float(extent), int(influence), ptr(grad_feat), ptr(partial),
+                         stream_ptr()), "cl3d_agg_bwd")
+    pg = reduce_partials(partial).view(P // C, C) if P > 0 else None
+    return grad_feat, pg
+
+
+def bn_finalize(bn_partial, C, count, eps, momentum, training, running_mean, running_var):
+    """-> save_stats (2,C): mean, invstd.  Updates running stats in place when training."""
+    dev = running_mean.device if running_mean is not None else bn_partial.device
+    stats = torch.empty(2, C, dtype=F32, device=dev)
+    nt = bn_partial.shape[0] if bn_partial is not None else 0
+    check(_lib.lib().cl3d_bn_finalize(ptr(bn_partial), nt, C, int(count), float(eps), float(momentum), int(training),
+                                      ptr(running_mean), ptr(running_var), ptr(stats), stream_ptr()),
+          "cl3d_bn_finalize")
+    return stats
+
+
+def bn_relu_fwd(x, stats, gamma, beta):
+    B, C, M = x.shape
+    y = torch.empty_like(x)
+    check(_lib.lib().cl3d_bn_relu_fwd(ptr(x), ptr(stats), ptr(gamma), ptr(beta), B, C, M, ptr(y), stream_ptr()),
+          "cl3d_bn_relu_fwd")
+    return y
+
+
+def bn_relu_bwd(grad_y, x, stats, gamma, beta, training):
+    """-> (g_pm (B,M,Cp) point-major d/d(agg), dgamma (C,), dbeta (C,))"""
+    B, C, M = x.shape
+    L = _lib.lib()
+    dev = x.device
+    partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, C, dtype=F32, device=dev)
+    dgb = torch.empty(2, C, dtype=F32, device=dev)
+    g_pm = torch.empty(B, M, padded_channels(C), dtype=F32, device=dev)
+    check(L.cl3d_bn_relu_bwd(ptr(grad_y), ptr(x), ptr(stats), ptr(gamma), ptr(beta), B, C, M, int(training),
+                             ptr(partial), ptr(dgb), ptr(g_pm), stream_ptr()), "cl3d_bn_relu_bwd")
+    return g_pm, dgb[0], dgb[1]

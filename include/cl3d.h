@@ -126,11 +126,12 @@ int cl3d_to_channel_major(const float* in_nc, int B, int C, int N, float* out_cn
  *
  * forward:  agg[b,c,q] = reduce_k  w_c(dp_k) * f[b, idx[b,q,k], c]      (never materialises (B,C,M,K))
  *   feat_pm   (B,N,Cp) point-major support features
- *   params    family parameters, fp32:
- *               POSPOOL_XYZ    : none (NULL)
- *               POSPOOL_SINCOS : dim_mat (C/6)         [torch.pow(1000, arange(F)/F), passed in for bit parity]
- *               ADAPTIVE_DP    : W (C/S,3) then b (C/S); `shared` = S
- *               PSEUDOGRID     : K_points (nkp,3) then kernel_weights (nkp,C); `extent`; `influence` 0=linear 1=constant
+ *   p0, p1    family parameters, fp32 (NULL when unused):
+ *               POSPOOL_XYZ    : -
+ *               POSPOOL_SINCOS : p0 = dim_mat (C/6)   [torch.pow(1000, arange(F)/F), passed in for bit parity]
+ *               ADAPTIVE_DP    : p0 = W (C/S,3), p1 = b (C/S); `shared` = S
+ *               PSEUDOGRID     : p0 = K_points (nkp,3), p1 = kernel_weights (nkp,C); `extent`;
+ *                                `influence` 0 = linear, 1 = constant
  *   normalize : 1 -> dp /= radius (pt_utils.py:128-129; PosPool/AdaptiveWeight), 0 -> raw (PseudoGrid)
  *   agg       (B,C,M) channel-major out (pre-BN)
  *   bn_partial (ntiles, 2, C) out: per-tile sum and sum of squares of agg (for the out_transform BN);
@@ -138,20 +139,25 @@ int cl3d_to_channel_major(const float* in_nc, int B, int C, int N, float* out_cn
  * backward (gather form over the CSR lists; no float atomics on activations):
  *   g_pm      (B,M,Cp) point-major d(loss)/d(agg)
  *   grad_feat (B,C,N) channel-major out, fully written
- *   grad_params_partial (nblocks_bwd, P) out: per-CTA partial parameter gradients (P = number of params),
- *               reduced by cl3d_reduce_partials; nblocks_bwd = cl3d_agg_num_tiles(B,N)
+ *   grad_params_partial (nblocks, P) out: per-CTA partial parameter gradients, nblocks =
+ *               cl3d_agg_bwd_num_blocks(B,N), P = cl3d_agg_num_params(...) laid out (slot, C) with
+ *               slot = {x,y,z,bias} (ADAPTIVE_DP, per channel: the caller folds `shared` groups) or the
+ *               kernel point (PSEUDOGRID); reduce with cl3d_reduce_partials.
+ * Only avg / sum reductions are fused (every shipped cfg uses avg; PseudoGrid is sum by construction).
  * ---------------------------------------------------------------------------------------------- */
 int cl3d_agg_num_tiles(int B, int M);
+int cl3d_agg_bwd_num_blocks(int B, int N);
 int cl3d_agg_num_params(int family, int C, int shared, int nkp);
 int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, const float* query_xyz,
-                 const float* support_xyz, const int* idx, const int* ncount, const float* params,
-                 int B, int N, int M, int K, int C, float radius, int normalize, int shared, int nkp,
-                 float extent, int influence, float* agg, float* bn_partial, cl3d_stream_t stream);
+                 const float* support_xyz, const int* idx, const int* ncount, const float* p0,
+                 const float* p1, int B, int N, int M, int K, int C, float radius, int normalize,
+                 int shared, int nkp, float extent, int influence, float* agg, float* bn_partial,
+                 cl3d_stream_t stream);
 int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const float* feat_pm,
                  const float* query_xyz, const float* support_xyz, const int* ncount,
-                 const int* csr_off, const int* csr_ent, const float* params, int B, int N, int M, int K,
-                 int C, float radius, int normalize, int shared, int nkp, float extent, int influence,
-                 float* grad_feat, float* grad_params_partial, cl3d_stream_t stream);
+                 const int* csr_off, const int* csr_ent, const float* p0, const float* p1, int B, int N,
+                 int M, int K, int C, float radius, int normalize, int shared, int nkp, float extent,
+                 int influence, float* grad_feat, float* grad_params_partial, cl3d_stream_t stream);
 /* out[p] = sum_t partial[t][p]  (fixed order -> deterministic given the partials) */
 int cl3d_reduce_partials(const float* partial, int ntiles, int P, float* out, cl3d_stream_t stream);
 
