@@ -45,12 +45,11 @@ SIGNATURES = {
     "cl3d_bn_finalize": (_i, [_vp, _i, _i, _ll, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "cl3d_bn_relu_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "cl3d_bn_relu_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "cl3d_sgemm_nt": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
-    "cl3d_pwmlp_fwd_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
-                                  _vp]),
+    "cl3d_sgemm_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cl3d_sgemm": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _i, _vp, _ll, _i, _vp, _sz, _vp]),
+    "cl3d_pwmlp_fwd_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "cl3d_pwmlp_fwd_out": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "cl3d_pwmlp_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "cl3d_pwmlp_bwd": (_i, [_vp] * 15 + [_i, _i, _i, _i, _i, _f, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "cl3d_pwmlp_bwd": (_i, [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -184,3 +184,60 @@ def bn_relu_bwd(grad_y, x, stats, gamma, beta, training):
     check(L.cl3d_bn_relu_bwd(ptr(grad_y), ptr(x), ptr(stats), ptr(gamma), ptr(beta), B, C, M, int(training),
                              ptr(partial), ptr(dgb), ptr(g_pm), stream_ptr()), "cl3d_bn_relu_bwd")
     return g_pm, dgb[0], dgb[1]
+
+
+# --------------------------------------------------------------------------------------------------
+# fp32 GEMM + fused PointWiseMLP
+# --------------------------------------------------------------------------------------------------
+def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1):
+    """out[m][n] = sum_k a[m*sa_m + k*sa_k] * b[k*sb_k + n*sb_n]  (element strides; fp32 FMA)"""
+    L = _lib.lib()
+    dev = a.device
+    ldc = N if ldc is None else ldc
+    if out is None:
+        out = torch.empty(M, ldc, dtype=F32, device=dev)
+    wsb = L.cl3d_sgemm_workspace_bytes(M, N, splitk)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if splitk > 1 else None
+    check(L.cl3d_sgemm(ptr(a), sa_m, sa_k, ptr(b), sb_k, sb_n, M, N, K, ptr(out), ldc, splitk, ptr(ws), wsb,
+                       stream_ptr()), "cl3d_sgemm")
+    return out
+
+
+def pwmlp_fwd_stats(ab_pm, wp, query_xyz, support_xyz, idx, Cout, radius):
+    B, N, _ = ab_pm.shape
+    M, K = idx.shape[1], idx.shape[2]
+    L = _lib.lib()
+    dev = ab_pm.device
+    Cop = padded_channels(Cout)
+    ymax = torch.empty(B, Cout, M, dtype=F32, device=dev)
+    ymin = torch.empty(B, Cout, M, dtype=F32, device=dev)
+    arg = torch.empty(B, M, Cop, dtype=torch.int16, device=dev)
+    partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, Cout, dtype=F32, device=dev)
+    check(L.cl3d_pwmlp_fwd_stats(ptr(ab_pm), ptr(wp), ptr(query_xyz), ptr(support_xyz), ptr(idx), B, N, M, K, Cout,
+                                 float(radius), ptr(ymax), ptr(ymin), ptr(arg), ptr(partial), stream_ptr()),
+          "cl3d_pwmlp_fwd_stats")
+    return ymax, ymin, arg, partial
+
+
+def pwmlp_fwd_out(ymax, ymin, stats, gamma, beta):
+    B, Cout, M = ymax.shape
+    out = torch.empty_like(ymax)
+    check(_lib.lib().cl3d_pwmlp_fwd_out(ptr(ymax), ptr(ymin), ptr(stats), ptr(gamma), ptr(beta), B, M, Cout, ptr(out),
+                                        stream_ptr()), "cl3d_pwmlp_fwd_out")
+    return out
+
+
+def pwmlp_bwd(grad_out, out, ab_pm, wp, query_xyz, support_xyz, idx, ymax, ymin, arg, stats, gamma, radius):
+    """-> (grad_ab_pm (B,N,2Cop), grad_wp (3,Cout), dgamma (Cout), dbeta (Cout))"""
+    B, N, C2 = ab_pm.shape
+    Cout, M, K = out.shape[1], out.shape[2], idx.shape[2]
+    L = _lib.lib()
+    dev = out.device
+    partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 3, Cout, dtype=F32, device=dev)
+    dgb = torch.empty(2, Cout, dtype=F32, device=dev)
+    grad_ab = torch.empty(B, N, C2, dtype=F32, device=dev)
+    grad_wp = torch.empty(3, Cout, dtype=F32, device=dev)
+    check(L.cl3d_pwmlp_bwd(ptr(grad_out), ptr(out), ptr(ab_pm), ptr(wp), ptr(query_xyz), ptr(support_xyz), ptr(idx),
+                           ptr(ymax), ptr(ymin), ptr(arg), ptr(stats), ptr(gamma), B, N, M, K, Cout, float(radius),
+                           ptr(partial), ptr(dgb), ptr(grad_ab), ptr(grad_wp), stream_ptr()), "cl3d_pwmlp_bwd")
+    return grad_ab, grad_wp, dgb[0], dgb[1]

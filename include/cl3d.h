@@ -186,24 +186,32 @@ int cl3d_bn_relu_bwd(const float* grad_y, const float* x, const float* save_stat
  * fly and the max over K is taken through the monotone BN+ReLU as relu(a*(a>=0?max:min)+b).
  * See DESIGN.md for the kernel list; entry points are declared in the PWMLP section below.
  * ---------------------------------------------------------------------------------------------- */
-/* C = A(rows x k) * B(k x cols), fp32 FMA (row-major, ld = cols of each): used for the per-point products */
-int cl3d_sgemm_nt(const float* a, int lda, const float* w, int ldw, int rows, int cols, int k, float* c,
-                  int ldc, cl3d_stream_t stream);
-int cl3d_pwmlp_fwd_stats(const float* a_pm, const float* bv_pm, const float* wp, const float* query_xyz,
+/* fp32 FMA GEMM with element strides and optional split-K (gemm.cu):
+ *   C[m][n] = sum_k A[m*sa_m + k*sa_k] * B[k*sb_k + n*sb_n],  C row stride ldc.
+ * splitk > 1 divides k among CTAs (fixed-order reduction); workspace = cl3d_sgemm_workspace_bytes. */
+size_t cl3d_sgemm_workspace_bytes(int M, int N, int splitk);
+int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k,
+               long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk, void* workspace,
+               size_t workspace_bytes, cl3d_stream_t stream);
+
+/* ab_pm (B,N,2*Cop): row = [A | Bv], Cop = cl3d_padded_channels(Cout);  wp (Cout,3) = conv weight columns 0..2.
+ * fwd_stats: ymax,ymin (B,Cout,M); arg (B,M,Cop) uint16 = argmax | argmin<<8 (K <= 255);
+ *            bn_partial (cl3d_agg_num_tiles(B,M), 2, Cout) -> cl3d_bn_finalize with count = B*M*K.
+ * fwd_out  : out (B,Cout,M) = relu(sc*(sc>=0 ? ymax : ymin) + sh).
+ * bwd      : partial = scratch (cl3d_agg_num_tiles(B,M), 3, Cout); dgamma_dbeta (2,Cout);
+ *            grad_ab_pm (B,N,2*Cop) (zero-filled by the call, then accumulated with fp32 red.add);
+ *            grad_wp (3,Cout). */
+int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* query_xyz,
                          const float* support_xyz, const int* idx, int B, int N, int M, int K, int Cout,
-                         float radius, float* ymax, float* ymin, unsigned char* amax, unsigned char* amin,
-                         float* bn_partial, cl3d_stream_t stream);
+                         float radius, float* ymax, float* ymin, unsigned short* arg, float* bn_partial,
+                         cl3d_stream_t stream);
 int cl3d_pwmlp_fwd_out(const float* ymax, const float* ymin, const float* save_stats, const float* gamma,
-                       const float* beta, int B, int M, int Cout, float* out /*(B,Cout,M)*/,
-                       cl3d_stream_t stream);
-int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* a_pm, const float* bv_pm,
-                   const float* wp, const float* query_xyz, const float* support_xyz, const int* idx,
-                   const float* ymax, const float* ymin, const unsigned char* amax,
-                   const unsigned char* amin, const float* save_stats, const float* gamma, int B, int N,
-                   int M, int K, int Cout, float radius, float* scratch, size_t scratch_bytes,
-                   float* grad_a_pm, float* grad_bv_pm, float* grad_small /* dWp(Cout,3), dgamma, dbeta */,
-                   cl3d_stream_t stream);
-size_t cl3d_pwmlp_bwd_scratch_bytes(int B, int N, int M, int K, int Cout);
+                       const float* beta, int B, int M, int Cout, float* out, cl3d_stream_t stream);
+int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, const float* wp,
+                   const float* query_xyz, const float* support_xyz, const int* idx, const float* ymax,
+                   const float* ymin, const unsigned short* arg, const float* save_stats,
+                   const float* gamma, int B, int N, int M, int K, int Cout, float radius, float* partial,
+                   float* dgamma_dbeta, float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -59,18 +59,22 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
         qm[:, M - M // 8:] = 0
     gout = torch.randn(B, C, q.shape[1], generator=torch.Generator().manual_seed(seed + 2))
 
-    # ---- oracle (CPU)
+    # ---- forward on both sides
     orc = la_oracle.OracleLocalAggregation(oracle_ext, la_type, C, C, r, K, cfg, sd)
     orc.training = train
     f_ref = feats.clone().requires_grad_(True)
     o_ref = orc(q, xyz, qm, mask, f_ref)
-    (o_ref * gout).sum().backward()
-
-    # ---- product (CUDA)
     mod = mod.to(cuda)
     mod.train(train)
     f = feats.to(cuda).requires_grad_(True)
     out = mod(q.to(cuda), xyz.to(cuda), qm.to(cuda), mask.to(cuda), f)
+    # The final ReLU makes the gradient discontinuous at 0: an output that is +4e-6 on one side and 0 on the
+    # other is inside the output tolerance but flips a whole BN channel's gradient.  Such elements (a handful
+    # per million) get zero upstream gradient on BOTH sides, so the comparison is well-posed.
+    flips = (out.detach().cpu() > 0) != (o_ref.detach() > 0)
+    assert int(flips.sum()) <= max(2, out.numel() // 100000), f"{int(flips.sum())} ReLU sign flips"
+    gout = gout * (~flips)
+    (o_ref * gout).sum().backward()
     (out * gout.to(cuda)).sum().backward()
     torch.cuda.synchronize()
 
@@ -94,6 +98,7 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     return e_out, e_gf
 
 
+PW = dict(pointwisemlp=dict(feature_type="dp_fi_df", num_mlps=1, reduction="max"))
 XYZ_AVG = dict(pospool=dict(position_embedding="xyz", reduction="avg"))
 SINCOS_AVG = dict(pospool=dict(position_embedding="sin_cos", reduction="avg"))
 AW = dict(adaptive_weight=dict(weight_type="dp", num_mlps=1, shared_channels=1, reduction="avg"))
@@ -113,6 +118,10 @@ AW = dict(adaptive_weight=dict(weight_type="dp", num_mlps=1, shared_channels=1, 
     ("pseudo_grid", dict(), 2, 3000, 26, 72),             # c3 operator shape, smaller cloud
     ("pseudo_grid", dict(pseudo_grid=dict(KP_influence="constant")), 2, 800, 16, 36),
     ("pseudo_grid", dict(), 2, 1500, 16, 144),            # two channel chunks
+    ("pointwisemlp", PW, 2, 1024, 16, 66),
+    ("pointwisemlp", PW, 4, 1024, 32, 72),                # c2 operator shape, smaller batch
+    ("pointwisemlp", PW, 2, 2500, 20, 36),
+    ("pointwisemlp", PW, 1, 600, 40, 144),                # two output-channel chunks, K > 32
 ])
 def test_family_matches_oracle(cuda, oracle_ext, la_type, over, B, N, K, C):
     # 'constant' influence + BatchNorm: every kernel weight only rescales its channel, which BN removes, so
@@ -121,7 +130,8 @@ def test_family_matches_oracle(cuda, oracle_ext, la_type, over, B, N, K, C):
     run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed=2000 + N + C, param_tol=ptol)
 
 
-@pytest.mark.parametrize("la_type,over", [("pospool", XYZ_AVG), ("adaptive_weight", AW), ("pseudo_grid", dict())])
+@pytest.mark.parametrize("la_type,over", [("pospool", XYZ_AVG), ("adaptive_weight", AW), ("pseudo_grid", dict()),
+                                          ("pointwisemlp", PW)])
 def test_strided_queries(cuda, oracle_ext, la_type, over):
     # queries != supports (strided bottleneck): M < N, padded queries, some queries with few neighbours
     run_case(cuda, oracle_ext, la_type, over, 3, 2400, 16, 72, seed=31, M=600, radius=0.15)
@@ -137,6 +147,7 @@ def test_eval_mode_uses_running_stats(cuda, oracle_ext, la_type, over):
     ("pospool", dict(pospool=dict(position_embedding="xyz", reduction="avg", output_conv=True))),
     ("adaptive_weight", dict(adaptive_weight=dict(num_mlps=2, shared_channels=2, reduction="avg"))),
     ("pseudo_grid", dict(pseudo_grid=dict(output_conv=True))),
+    ("pointwisemlp", dict(pointwisemlp=dict(feature_type="dp_fi_df", num_mlps=2, reduction="max"))),
 ])
 def test_composed_settings(cuda, oracle_ext, la_type, over):
     # settings outside the fused kernels run through the materialising GPU path (library conv: TF32 off)
