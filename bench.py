@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- local-aggregation hot path: points/s (forward + backward) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one LocalAggregation call of the BASELINE.json configuration (default configs[1]:
+ModelNet40 Point-wise MLP, B=32 N=1024 K=32 C=72 per GPU), forward AND backward (gradients w.r.t. the input
+features and every parameter), INCLUDING the neighbour search (the neighbour-list cache is disabled, so no
+step re-uses the previous step's search), on a fresh synthetic batch: a ring of pre-generated batches larger
+than the 126 MB L2 is rotated so that no step finds its inputs in L2.  Multi-GPU: batches shard over ranks
+(weak scaling: B per GPU is fixed), the only exchange is the NCCL all-reduce of parameter gradients.
+
+The JSON line follows the driver contract; extra objects:
+  roofline      dominant kernel (by CUDA-event time) : achieved algorithmic GB/s vs the measured HBM peak
+  cpu_baseline  the oracle port of the reference path on this box's host cores, bounded sample
+  e2e           same metric through the public module API from pinned HOST buffers (H2D + D2H inside)
+  ref_gpu       (informational) the reference's own CUDA extension (oracle/_ref) under the unfused python layer
+`--impl reference` prints the reference arm: the reference's algorithm on the host cores (oracle port; the
+reference's native ops are CUDA-only, every entry point is TORCH_CHECK(false, "CPU not supported")).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index 1..5 (default 2 = configs[1])")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default: the config's B, or B/8 for 8-GPU configs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# algorithmic (compulsory) HBM bytes per POINT of each entry point, see DESIGN.md "Kernels"
+def algo_bytes_per_point(name, C, K, Cout):
+    Cop = (Cout + 7) & ~7
+    table = {
+        "cl3d_ball_query_algo": 16 + 16 + 4 * K + 4,            # support xyz+mask, query xyz+mask, idx, ncount
+        "cl3d_to_point_major": 8 * C,
+        "cl3d_to_channel_major": 8 * C,
+        "cl3d_agg_fwd": 8 * C + 4 * K + 20,                    # f row in, agg out, idx, xyz, ncount
+        "cl3d_agg_bwd": 8 * C + 4 * K + 20,
+        "cl3d_bn_relu_fwd": 8 * C,
+        "cl3d_bn_relu_bwd": 12 * C + 8 * C,                    # (grad_y, x) twice, g_pm out
+        "cl3d_build_csr": 12 * K + 8,
+        "cl3d_sgemm": 4 * C + 8 * Cop,
+        "cl3d_pwmlp_fwd_stats": 8 * Cop + 8 * Cout + 2 * Cop + 4 * K + 16,
+        "cl3d_pwmlp_fwd_out": 8 * Cout,
+        "cl3d_pwmlp_bwd": 16 * Cout + 8 * Cop + 2 * Cop + 4 * K + 16 + 16 * Cop,
+    }
+    return table.get(name)
+
+
+def build_module(spec, device):
+    import numpy as np
+    from closerlook3d_b200.local_aggregation_operators import LocalAggregation
+    from closerlook3d_b200 import synth
+    i = spec["index"]
+    torch.manual_seed(2000 + i)
+    np.random.seed(2000 + i)
+    r = synth.ball_radius(spec["N"], spec["K"])
+    mod = LocalAggregation(spec["C"], spec["C"], r, spec["K"], spec["cfg"])
+    return mod.to(device), r
+
+
+def make_ring(spec, B_local, rank, device, min_bytes, pinned=False):
+    """pre-generated batches; total size > min_bytes so consecutive steps never hit L2-resident inputs"""
+    from closerlook3d_b200 import synth
+    per = B_local * spec["N"] * (12 + 4 + 4 * spec["C"])
+    n = max(2, int(min_bytes // per) + 1)
+    n = min(n, 64)
+    ring = []
+    for t in range(n):
+        d = synth.make_cloud_batch(B_local, spec["N"], spec["C"], 1000 + spec["index"] + 7919 * t + 104729 * rank,
+                                   b_offset=rank * B_local)
+        if pinned:
+            ring.append({k: v.pin_memory() for k, v in d.items()})
+        else:
+            ring.append({k: v.to(device) for k, v in d.items()})
+    return ring
+
+
+def run_ours(args, spec, rank, world, device):
+    from closerlook3d_b200 import _lib, pt_utils
+    import torch.distributed as dist
+    pt_utils.cache_enabled = False  # every step searches its neighbours again (no cached outputs)
+    B_local = args.batch or (spec["B"] if spec["gpus"] == 1 else max(1, spec["B"] // spec["gpus"]))
+    mod, radius = build_module(spec, device)
+    mod.train()
+    L2 = 126e6
+    ring = make_ring(spec, B_local, rank, device, 1.6 * L2)
+    C, N, K = spec["C"], spec["N"], spec["K"]
+    gout = torch.randn(B_local, C, N, device=device, generator=torch.Generator(device=device).manual_seed(5))
+    params = [p for p in mod.parameters()]
+
+    def step(batch, reduce_grads=True):
+        f = batch["features"]
+        f.requires_grad_(True)
+        f.grad = None
+        for p in params:
+            p.grad = None
+        out = mod(batch["xyz"], batch["xyz"], batch["mask"], batch["mask"], f)
+        out.backward(gout)
+        if world > 1 and reduce_grads:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        return out
+
+    for w in range(args.warmup):
+        step(ring[w % len(ring)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    L = _lib.lib()
+    launches0 = L.cl3d_launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        b = ring[(args.warmup + s) % len(ring)]
+        ev[s][0].record()
+        step(b)
+        ev[s][1].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = L.cl3d_launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    pts_per_step = B_local * N * world
+    value = pts_per_step / (ms_per_step * 1e-3)
+
+    # ---- per-entry-point device time (separate identical pass, CUDA events on the launch stream)
+    prof = None
+    if rank == 0:
+        _lib.profiler.start()
+        for s in range(args.steps):
+            step(ring[(args.warmup + s) % len(ring)], reduce_grads=False)
+        prof = _lib.profiler.stop()
+
+    # ---- end to end through the public API from pinned host buffers
+    e2e = None
+    hring = make_ring(spec, B_local, rank, device, 0.0, pinned=True)
+    h2d = sum(v.numel() * v.element_size() for v in hring[0].values())
+    nst = max(5, min(args.steps, 30))
+
+    def e2e_step(hb):
+        b = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
+        out = step(b)
+        return float(out.sum().item())  # D2H read of the step's result
+
+    for w in range(3):
+        e2e_step(hring[w % len(hring)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(nst):
+        e2e_step(hring[s % len(hring)])
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": pts_per_step * nst / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": 4, "steps": nst, "timing": "host wall clock around H2D + step + D2H, max over ranks"}
+    return dict(value=value, ms_per_step=ms_per_step, clocks=clocks, launches=int(launches), prof=prof, e2e=e2e,
+                B_local=B_local, wall_s=t_wall, mod=mod, radius=radius, ring=ring)
+
+
+def cpu_reference_arm(spec, steps, warmup, budget_s=25.0):
+    """the reference's algorithm on the host cores: oracle port (C/OpenMP restatement of the CUDA ops under the
+    unfused python layer), forward + backward, on a bounded sample of the workload"""
+    import oracle
+    oracle.build()
+    from oracle import ext as oext, la_oracle
+    from closerlook3d_b200 import synth
+    from closerlook3d_b200.local_aggregation_operators import LocalAggregation
+    import numpy as np
+    torch.set_num_threads(os.cpu_count())
+    i = spec["index"]
+    torch.manual_seed(2000 + i)
+    np.random.seed(2000 + i)
+    r = synth.ball_radius(spec["N"], spec["K"])
+    sd = LocalAggregation(spec["C"], spec["C"], r, spec["K"], spec["cfg"]).state_dict()
+    # bounded sample: as many clouds of the workload as fit ~budget_s
+    Bs = min(spec["B"], 2)
+    orc = la_oracle.OracleLocalAggregation(oext, spec["la"], spec["C"], spec["C"], r, spec["K"], spec["cfg"], sd)
+
+    def one(B):
+        d = synth.make_cloud_batch(B, spec["N"], spec["C"], 1000 + i)
+        f = d["features"].requires_grad_(True)
+        t0 = time.perf_counter()
+        out = orc(d["xyz"], d["xyz"], d["mask"], d["mask"], f)
+        out.backward(torch.ones_like(out))
+        return time.perf_counter() - t0
+
+    t = one(Bs)  # warm-up + calibration
+    per_cloud = t / Bs
+    n_steps = max(1, steps)
+    Bs = int(max(1, min(spec["B"], budget_s / max(per_cloud, 1e-6) / (n_steps + max(0, warmup)))))
+    for _ in range(max(0, warmup)):
+        one(Bs)
+    ts = [one(Bs) for _ in range(n_steps)]
+    sec = sum(ts) / len(ts)
+    return {"value": Bs * spec["N"] / sec, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+            "threads_openmp": oext.num_threads(), "ms_per_step": sec * 1e3,
+            "sample": f"{Bs} of {spec['B']} clouds of the workload per step, fwd+bwd, {n_steps} steps"}
+
+
+def ref_gpu_arm(spec, device, res):
+    """informational: the reference's OWN CUDA extension (compiled unmodified into oracle/_ref) under the unfused
+    python layer (oracle/la_oracle.py) on the same GPU and inputs.  TF32 off."""
+    try:
+        from oracle import build_ref, la_oracle
+        ext = build_ref.load()
+    except Exception as e:
+        return {"unavailable": str(e)[:200]}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mod = res["mod"]
+    orc = la_oracle.OracleLocalAggregation(ext, spec["la"], spec["C"], spec["C"], res["radius"], spec["K"], spec["cfg"],
+                                           mod.state_dict(), device=device)
+    ring = res["ring"]
+    B, N, C = res["B_local"], spec["N"], spec["C"]
+    gout = torch.ones(B, C, N, device=device)
+
+    def one(b):
+        f = b["features"].detach().clone().requires_grad_(True)
+        out = orc(b["xyz"], b["xyz"], b["mask"], b["mask"], f)
+        out.backward(gout)
+
+    try:
+        for w in range(2):
+            one(ring[w % len(ring)])
+        torch.cuda.synchronize()
+        n = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(n):
+            one(ring[(2 + s) % len(ring)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return {"value": B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms,
+                "what": "reference CUDA ext (sm_100, unmodified) + unfused python layer, 1 GPU, fwd+bwd"}
+    except Exception as e:  # e.g. out of memory on the inflated tensors
+        return {"unavailable": str(e)[:200]}
+
+
+def main():
+    args = parse()
+    from closerlook3d_b200.config import baseline_config
+    spec = baseline_config(args.config)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "aggregated points/sec (fwd+bwd), one LocalAggregation call incl. neighbour search"
+    workload = f"configs[{args.config - 1}]: {spec['name']} B={spec['B']} N={spec['N']} K={spec['K']} C={spec['C']}"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_reference_arm(spec, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "family": spec["la"], "arm": "reference algorithm on host cores"},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    res = run_ours(args, spec, rank, world, device)
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    C, K, N = spec["C"], spec["K"], spec["N"]
+    pts_local = res["B_local"] * N
+    prof = res["prof"] or {}
+    kern = []
+    for name, (calls, ms) in prof.items():
+        ab = algo_bytes_per_point(name, C, K, C)
+        per_launch_ms = ms / max(1, calls)
+        kern.append({"entry": name, "calls_per_step": calls / args.steps, "ms_per_step": ms / args.steps,
+                     "ms_per_call": per_launch_ms,
+                     "algo_gbs": (ab * pts_local / (per_launch_ms * 1e-3) / 1e9) if ab and per_launch_ms > 0 else None})
+    kern.sort(key=lambda k: -k["ms_per_step"])
+    roof = None
+    if kern:
+        top = kern[0]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(f"c{args.config}", {}).get(top["entry"])
+        roof = {"bound": "hbm", "kernel": top["entry"], "achieved": top["algo_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": (top["algo_gbs"] / peak) if top["algo_gbs"] else None, "traffic": traffic,
+                "peak_source": peak_src, "share_of_step": top["ms_per_step"] / max(1e-9, sum(k["ms_per_step"] for k in kern)),
+                "step_algo_bytes_per_point": 16 * C + 8 * K + 32,
+                "step_frac": (16 * C + 8 * K + 32) * res["value"] / world / 1e9 / peak}
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_reference_arm(spec, 3, 1, budget_s=15.0)
+    rg = None
+    if not args.no_ref_gpu:
+        rg = ref_gpu_arm(spec, device, res)
+    line = {"metric": metric, "value": res["value"], "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "family": spec["la"], "clouds_per_gpu": res["B_local"],
+                       "points_per_step": pts_local * world, "parallelism": f"dp{world}",
+                       "l2": "inputs rotate over a ring of pre-generated batches > 1.6x L2 (126 MB)",
+                       "neighbour_cache": "disabled (search runs every step)"},
+            "clocks": res["clocks"], "gpu_launches": res["launches"], "e2e": res["e2e"], "roofline": roof,
+            "cpu_baseline": cb, "kernels": kern[:8], "ref_gpu": rg}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

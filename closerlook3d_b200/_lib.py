@@ -22,6 +22,7 @@ SIGNATURES = {
     "cl3d_last_error": (ctypes.c_char_p, []),
     "cl3d_padded_channels": (_i, [_i]),
     "cl3d_sm_count": (_i, []),
+    "cl3d_launch_count": (_ll, []),
     "cl3d_ball_query_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cl3d_ball_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cl3d_ball_query_algo": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
@@ -53,6 +54,56 @@ SIGNATURES = {
 }
 
 
+class _Profiler:
+    """optional per-entry-point CUDA-event timing (bench.py): events are recorded on torch's current stream,
+    the stream every kernel of the call is launched on."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []  # (name, start_event, end_event)
+
+    def start(self):
+        self.records = []
+        self.enabled = True
+
+    def stop(self):
+        """-> {entry point: (calls, total_ms)}; synchronises"""
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        self.records = []
+        return out
+
+
+profiler = _Profiler()
+
+
+class _Lib:
+    pass
+
+
+def _wrap(name, fn):
+    def call(*args):
+        if profiler.enabled and name not in _UNTIMED:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            profiler.records.append((name, e0, e1))
+            return rc
+        return fn(*args)
+    return call
+
+
+_UNTIMED = {"cl3d_version", "cl3d_last_error", "cl3d_padded_channels", "cl3d_sm_count", "cl3d_launch_count",
+            "cl3d_ball_query_workspace_bytes", "cl3d_csr_workspace_bytes", "cl3d_grid_subsample_workspace_bytes",
+            "cl3d_agg_num_tiles", "cl3d_agg_bwd_num_blocks", "cl3d_agg_num_params", "cl3d_sgemm_workspace_bytes"}
+
+
 def lib():
     """Load libcl3d.so (built in-tree by closerlook3d_b200/build.py).  Raises ImportError if absent."""
     global _lib
@@ -61,11 +112,14 @@ def lib():
             raise ImportError(
                 f"{SO_PATH} not found: build it with `python -m closerlook3d_b200.build` "
                 "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback.")
-        L = ctypes.CDLL(SO_PATH)
+        cdll = ctypes.CDLL(SO_PATH)
+        L = _Lib()
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)  # AttributeError if the symbol is missing -> loud
+            fn = getattr(cdll, name)  # AttributeError if the symbol is missing -> loud
             fn.restype = res
             fn.argtypes = args
+            setattr(L, name, _wrap(name, fn))
+        L._cdll = cdll
         _lib = L
     return _lib
 

@@ -506,7 +506,7 @@ static int launch_fwd(const AggArgs& a, cudaStream_t stream) {
   const SmemLayout L = smem_layout(a.K, 32 * CI, FAM == CL3D_FAM_PSEUDOGRID, 0);
   cudaFuncSetAttribute(agg_fwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   dim3 grid(a.ntiles, nchunks);
-  agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a); CL3D_LAUNCHED(1);
   return check_launch("agg_fwd_kernel");
 }
 
@@ -517,7 +517,7 @@ static int launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   const SmemLayout L = smem_layout(a.rows_per_stage, 32 * CI, FAM == CL3D_FAM_PSEUDOGRID, ppc * 32 * CI);
   cudaFuncSetAttribute(agg_bwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   dim3 grid(grid_x, nchunks);
-  agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a); CL3D_LAUNCHED(1);
   return check_launch("agg_bwd_kernel");
 }
 

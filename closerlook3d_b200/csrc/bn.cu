@@ -183,7 +183,7 @@ extern "C" int cl3d_bn_finalize(const float* bn_partial, int ntiles, int C, long
   CL3D_REQUIRE(training || (running_mean && running_var), "cl3d_bn_finalize: eval needs running statistics");
   bn_finalize_kernel<<<ceil_div(C, 32), 1024, 0, (cudaStream_t)stream_>>>(bn_partial, ntiles, C, (double)count, eps,
                                                                          momentum, training, running_mean,
-                                                                         running_var, save_stats);
+                                                                         running_var, save_stats); CL3D_LAUNCHED(1);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -194,7 +194,7 @@ extern "C" int cl3d_bn_relu_fwd(const float* x, const float* save_stats, const f
   int chunks = ceil_div(M, 1024);
   chunks = chunks < 1 ? 1 : (chunks > 65535 ? 65535 : chunks);
   dim3 grid(B * C, chunks);
-  bn_relu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, save_stats, gamma, beta, C, M, y);
+  bn_relu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, save_stats, gamma, beta, C, M, y); CL3D_LAUNCHED(1);
   return check_launch("bn_relu_fwd_kernel");
 }
 
@@ -208,12 +208,12 @@ extern "C" int cl3d_bn_relu_bwd(const float* grad_y, const float* x, const float
   if (B == 0) return CL3D_OK;
   const int ntiles = B * ceil_div(M, kBnTile);
   const int Cp = padded_channels(C);
-  bn_relu_bwd_stats_kernel<<<ntiles, 256, 0, stream>>>(grad_y, x, save_stats, gamma, beta, C, M, partial);
-  bn_reduce2_kernel<<<ceil_div(C, 32), 1024, 0, stream>>>(partial, ntiles, C, dgamma_dbeta);
+  bn_relu_bwd_stats_kernel<<<ntiles, 256, 0, stream>>>(grad_y, x, save_stats, gamma, beta, C, M, partial); CL3D_LAUNCHED(1);
+  bn_reduce2_kernel<<<ceil_div(C, 32), 1024, 0, stream>>>(partial, ntiles, C, dgamma_dbeta); CL3D_LAUNCHED(1);
   const size_t smem = (size_t)kBnTile * (Cp + 1) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(bn_relu_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   bn_relu_bwd_apply_kernel<<<ntiles, 256, smem, stream>>>(grad_y, x, save_stats, gamma, beta, dgamma_dbeta, C, Cp, M,
-                                                          1.0f / (float)((long long)B * M), training, g_pm);
+                                                          1.0f / (float)((long long)B * M), training, g_pm); CL3D_LAUNCHED(1);
   return check_launch("bn_relu_bwd kernels");
 }

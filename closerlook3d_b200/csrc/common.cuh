@@ -35,6 +35,10 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 int sm_count();
 
+// number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
+void count_launches(int n);
+#define CL3D_LAUNCHED(n) ::cl3d::count_launches(n)
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

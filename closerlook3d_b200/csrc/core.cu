@@ -7,6 +7,8 @@
 namespace cl3d {
 
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -138,6 +140,7 @@ extern "C" int cl3d_version(void) { return 100; }
 extern "C" const char* cl3d_last_error(void) { return g_err; }
 extern "C" int cl3d_padded_channels(int C) { return padded_channels(C); }
 extern "C" int cl3d_sm_count(void) { return sm_count(); }
+extern "C" long long cl3d_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int cl3d_to_point_major(const float* in_cn, int B, int C, int N, float* out_nc, cl3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -145,7 +148,7 @@ extern "C" int cl3d_to_point_major(const float* in_cn, int B, int C, int N, floa
   if (B == 0) return CL3D_OK;
   const int Cp = padded_channels(C);
   dim3 grid(ceil_div(N, 32), ceil_div(Cp, 32), B);
-  to_point_major_kernel<<<grid, 256, 0, stream>>>(in_cn, C, N, Cp, out_nc);
+  to_point_major_kernel<<<grid, 256, 0, stream>>>(in_cn, C, N, Cp, out_nc); CL3D_LAUNCHED(1);
   return check_launch("to_point_major_kernel");
 }
 
@@ -155,7 +158,7 @@ extern "C" int cl3d_to_channel_major(const float* in_nc, int B, int C, int N, fl
   if (B == 0) return CL3D_OK;
   const int Cp = padded_channels(C);
   dim3 grid(ceil_div(N, 32), ceil_div(C, 32), B);
-  to_channel_major_kernel<<<grid, 256, 0, stream>>>(in_nc, C, N, Cp, out_cn);
+  to_channel_major_kernel<<<grid, 256, 0, stream>>>(in_nc, C, N, Cp, out_cn); CL3D_LAUNCHED(1);
   return check_launch("to_channel_major_kernel");
 }
 
@@ -167,7 +170,7 @@ extern "C" int cl3d_group_points(const float* points, const int* idx, int B, int
   if (B == 0 || M == 0) return CL3D_OK;
   const long long ents = (long long)M * K;
   dim3 grid((unsigned)((ents + 255) / 256), C, B);
-  group_points_kernel<<<grid, 256, 0, stream>>>(points, idx, C, N, M, K, out);
+  group_points_kernel<<<grid, 256, 0, stream>>>(points, idx, C, N, M, K, out); CL3D_LAUNCHED(1);
   return check_launch("group_points_kernel");
 }
 
@@ -182,13 +185,13 @@ extern "C" int cl3d_group_points_grad(const float* grad_out, const int* idx, int
   if (M == 0) return CL3D_OK;
   const long long ents = (long long)M * K;
   dim3 grid((unsigned)((ents + 255) / 256), C, B);
-  group_points_grad_kernel<<<grid, 256, 0, stream>>>(grad_out, idx, C, N, M, K, grad_points);
+  group_points_grad_kernel<<<grid, 256, 0, stream>>>(grad_out, idx, C, N, M, K, grad_points); CL3D_LAUNCHED(1);
   return check_launch("group_points_grad_kernel");
 }
 
 extern "C" int cl3d_reduce_partials(const float* partial, int ntiles, int P, float* out, cl3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   CL3D_REQUIRE(ntiles >= 0 && P >= 1 && partial && out, "cl3d_reduce_partials: bad arguments");
-  reduce_partials_kernel<<<ceil_div(P, 32), 1024, 0, stream>>>(partial, ntiles, P, out);
+  reduce_partials_kernel<<<ceil_div(P, 32), 1024, 0, stream>>>(partial, ntiles, P, out); CL3D_LAUNCHED(1);
   return check_launch("reduce_partials_kernel");
 }

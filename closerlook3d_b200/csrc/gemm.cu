@@ -112,10 +112,10 @@ extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const 
     partial = (float*)workspace;
   }
   dim3 grid(ceil_div(N, kGN), ceil_div(M, kGM), splitk);
-  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial);
+  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); CL3D_LAUNCHED(1);
   if (splitk > 1) {
     const long long total = (long long)M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splitk, M, N, c, ldc);
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splitk, M, N, c, ldc); CL3D_LAUNCHED(1);
   }
   return check_launch("sgemm_strided_kernel");
 }

@@ -600,7 +600,7 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
     }
     dim3 grid(ceil_div(M, qpc), B);
     ball_query_brute_kernel<<<grid, kBQWarps * 32, smem, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
-                                                                   N, M, radius, K, qpc, idx, idx_mask, ncount);
+                                                                   N, M, radius, K, qpc, idx, idx_mask, ncount); CL3D_LAUNCHED(1);
     return check_launch("ball_query_brute_kernel");
   }
   if (workspace_bytes < cl3d_ball_query_workspace_bytes(B, N, M, K) || !workspace) {
@@ -620,12 +620,12 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
   w += align_up(sizeof(int2) * (size_t)B * N, 256);
   float4* sorted = (float4*)w;
 
-  grid_params_kernel<<<B, 1024, 0, stream>>>(support_xyz, support_mask, N, radius, cap, params);
-  zero_cells_kernel<<<dim3(64, B), 256, 0, stream>>>(params, cap, cell_cnt);
-  cell_count_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_cnt, cell_rank);
-  cell_scan_kernel<<<B, 1024, 0, stream>>>(params, cap, cell_cnt, cell_start);
+  grid_params_kernel<<<B, 1024, 0, stream>>>(support_xyz, support_mask, N, radius, cap, params); CL3D_LAUNCHED(1);
+  zero_cells_kernel<<<dim3(64, B), 256, 0, stream>>>(params, cap, cell_cnt); CL3D_LAUNCHED(1);
+  cell_count_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_cnt, cell_rank); CL3D_LAUNCHED(1);
+  cell_scan_kernel<<<B, 1024, 0, stream>>>(params, cap, cell_cnt, cell_start); CL3D_LAUNCHED(1);
   cell_fill_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_start, cell_rank,
-                                                                  sorted);
+                                                                  sorted); CL3D_LAUNCHED(1);
   size_t smem = (size_t)kBQWarps * (kCandCap + cap3k) * 8 + (size_t)kBQWarps * K * 4;
   static bool attr_set2 = false;
   if (!attr_set2) {
@@ -634,7 +634,7 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
   }
   const long long total = (long long)B * M;
   ball_query_grid_kernel<<<(unsigned)((total + kBQWarps - 1) / kBQWarps), kBQWarps * 32, smem, stream>>>(
-      query_xyz, support_xyz, query_mask, params, cell_start, sorted, B, N, M, radius, K, cap, idx, idx_mask, ncount);
+      query_xyz, support_xyz, query_mask, params, cell_start, sorted, B, N, M, radius, K, cap, idx, idx_mask, ncount); CL3D_LAUNCHED(1);
   return check_launch("ball_query_grid_kernel");
 }
 
@@ -647,7 +647,7 @@ extern "C" int cl3d_nearest_query(const float* query_xyz, const float* support_x
                "cl3d_nearest_query: null pointer");
   if (B == 0 || M == 0) return CL3D_OK;
   nearest_query_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
-                                                                      N, M, idx, idx_mask);
+                                                                      N, M, idx, idx_mask); CL3D_LAUNCHED(1);
   return check_launch("nearest_query_kernel");
 }
 
@@ -672,11 +672,11 @@ extern "C" int cl3d_build_csr(const int* idx, const int* ncount, int B, int N, i
   cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)B * N, stream);
   const long long ents = (long long)M * K;
   if (ents > 0) {
-    csr_count_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, N, M, K, cnt);
+    csr_count_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, N, M, K, cnt); CL3D_LAUNCHED(1);
   }
-  csr_scan_kernel<<<B, 1024, 0, stream>>>(N, cnt, csr_off, cursor);
+  csr_scan_kernel<<<B, 1024, 0, stream>>>(N, cnt, csr_off, cursor); CL3D_LAUNCHED(1);
   if (ents > 0) {
-    csr_fill_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, N, M, K, cursor, csr_ent);
+    csr_fill_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, N, M, K, cursor, csr_ent); CL3D_LAUNCHED(1);
   }
   return check_launch("csr kernels");
 }

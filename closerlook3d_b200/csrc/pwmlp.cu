@@ -402,7 +402,7 @@ static int launch_pw_fwd(const PwArgs& a, cudaStream_t stream) {
   const PwSmem L = pw_smem(a.K, 32 * CI);
   cudaFuncSetAttribute(pwmlp_fwd_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   dim3 grid(a.ntiles, ceil_div(a.Cop, 32 * CI));
-  pwmlp_fwd_kernel<CI><<<grid, kPWWarps * 32, L.total, stream>>>(a);
+  pwmlp_fwd_kernel<CI><<<grid, kPWWarps * 32, L.total, stream>>>(a); CL3D_LAUNCHED(1);
   return check_launch("pwmlp_fwd_kernel");
 }
 template <int CI>
@@ -410,7 +410,7 @@ static int launch_pw_bwd(const PwArgs& a, cudaStream_t stream) {
   const PwSmem L = pw_smem(a.K, 32 * CI);
   cudaFuncSetAttribute(pwmlp_bwd_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   dim3 grid(a.ntiles, ceil_div(a.Cop, 32 * CI));
-  pwmlp_bwd_kernel<CI><<<grid, kPWWarps * 32, L.total, stream>>>(a);
+  pwmlp_bwd_kernel<CI><<<grid, kPWWarps * 32, L.total, stream>>>(a); CL3D_LAUNCHED(1);
   return check_launch("pwmlp_bwd_kernel");
 }
 
@@ -460,7 +460,7 @@ extern "C" int cl3d_pwmlp_fwd_out(const float* ymax, const float* ymin, const fl
   int chunks = ceil_div(M, 1024);
   chunks = chunks < 1 ? 1 : (chunks > 65535 ? 65535 : chunks);
   pwmlp_out_kernel<<<dim3(B * Cout, chunks), 256, 0, (cudaStream_t)stream_>>>(ymax, ymin, save_stats, gamma, beta,
-                                                                             Cout, M, out);
+                                                                             Cout, M, out); CL3D_LAUNCHED(1);
   return check_launch("pwmlp_out_kernel");
 }
 
@@ -479,7 +479,7 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   if (B == 0) return CL3D_OK;
   const int ntiles = B * ceil_div(M, kPWTile);
   const int Cop = padded_channels(Cout);
-  pwmlp_bwd_stats_kernel<<<ntiles, 256, 0, stream>>>(grad_out, out, ymax, ymin, save_stats, gamma, Cout, M, partial);
+  pwmlp_bwd_stats_kernel<<<ntiles, 256, 0, stream>>>(grad_out, out, ymax, ymin, save_stats, gamma, Cout, M, partial); CL3D_LAUNCHED(1);
   // dgamma_dbeta[0] = sum dz*yhat (dgamma), [1] = sum dz (dbeta)
   int rc = cl3d_reduce_partials(partial, ntiles, 2 * Cout, dgamma_dbeta, stream_);
   if (rc) return rc;

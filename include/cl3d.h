@@ -58,6 +58,8 @@ const char* cl3d_last_error(void);
 int cl3d_padded_channels(int C);
 /* number of SMs of the current device (grid sizing); negative on error */
 int cl3d_sm_count(void);
+/* kernels launched by this library in this process so far (for bench.py's gpu_launches) */
+long long cl3d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Neighbour search.  Replaces _ext.masked_ordered_ball_query (masked_ordered_ball_query.cpp:13-59,
