@@ -9,24 +9,28 @@
 // none of which exists as a fused kernel there: the reference materialises (B,C,M,K) tensors ~10 times.
 //
 // Forward  (one warp per query, 32 consecutive queries per CTA):
-//   lanes load the query's neighbour indices, gather the neighbours' xyz, build dp = (s - q) * (1/r);
-//   every lane then issues one bulk async copy (cp.async.bulk, TMA non-tensor form) per neighbour ROW of
-//   the point-major feature matrix into shared memory, completion on an mbarrier; the warp multiplies by
-//   the family weight w_c(dp_k) and reduces over K in registers (lane = channel), so only the aggregated
-//   (B,C,M) tensor is written -- transposed through shared memory into the reference's channel-major
-//   layout, together with per-tile BatchNorm partial sums.
+//   lanes load the query's neighbour indices, gather the neighbours' xyz and build dp = (s - q) * (1/r) in
+//   shared memory (32 slots per round); the warp then streams the neighbours' ROWS of the point-major
+//   feature matrix with coalesced read-only loads (lane = channel, U rows in flight per lane), multiplies by
+//   the family weight w_c(dp_k) and reduces over K in registers, so only the aggregated (B,C,M) tensor is
+//   written -- transposed through shared memory into the reference's channel-major layout, together with
+//   per-tile BatchNorm partial sums.
 // Backward (gather form, one warp per SUPPORT point over its CSR list of (query, slot) references):
-//   rows of d(loss)/d(agg) are bulk-copied the same way; no float atomics on activations; parameter
-//   gradients are accumulated per CTA and reduced afterwards in a fixed order.
+//   rows of d(loss)/d(agg) are streamed the same way; no float atomics on activations; parameter gradients
+//   are accumulated per CTA and reduced afterwards in a fixed order.
+//
+// r1a staged the rows with one cp.async.bulk (TMA) per row; ncu showed that design issue-bound (UBLKCP is a
+// uniform instruction: ~11 warp-instructions per 288-byte row, plus the LDS to read it back), 3-5x slower than
+// this version.  See profiles/r1a_pwmlp_fwd_tma_summary.md.
 #include "common.cuh"
 
 namespace cl3d {
 
 constexpr int kAggWarps = 8;
-constexpr int kTile = 32;          // queries (fwd) / support points (bwd) per CTA tile
-constexpr int kStageBytes = 8192;  // bulk-copy staging per warp
-constexpr int kMaxKP = 16;         // PseudoGrid kernel points (reference default 15)
-constexpr int kMaxCI = 6;          // channel chunk = 32*CI <= 192 channels per CTA
+constexpr int kTile = 32;   // queries (fwd) / support points (bwd) per CTA tile
+constexpr int kMaxKP = 16;  // PseudoGrid kernel points (reference default 15)
+constexpr int kMaxCI = 6;   // channel chunk = 32*CI <= 192 channels per CTA
+constexpr int kSlots = 32;  // neighbour slots (fwd) / CSR entries (bwd) staged per round
 
 struct AggArgs {
   const float* feat_pm;      // (B,N,Cp)   fwd: features; bwd: features (for parameter gradients)
@@ -43,8 +47,7 @@ struct AggArgs {
   float* partial;            // fwd: bn partial (ntiles,2,C); bwd: param-grad partial (gridDim.x, P)
   int B, N, M, K, C, Cp;
   int reduction, normalize, shared, nkp, influence;
-  float inv_radius, extent, inv_extent;
-  int rows_per_stage;        // bulk-copy rows per stage for this channel chunk
+  float inv_radius, extent;
   int ntiles;
 };
 
@@ -71,15 +74,15 @@ __device__ __forceinline__ void load_lane_params(LaneParams<FAM, CI>& lp, const 
     lp.b[i] = lp.c[i] = lp.d[i] = 0.f;
     lp.is_cos[i] = 0;
     if (c >= a.C) continue;
-    if (FAM == CL3D_FAM_POSPOOL_XYZ) {
+    if constexpr (FAM == CL3D_FAM_POSPOOL_XYZ) {
       lp.axis[i] = c % 3;  // view(B, C//3, 3, ...) : local_aggregation_operators.py:67
-    } else if (FAM == CL3D_FAM_POSPOOL_SINCOS) {
+    } else if constexpr (FAM == CL3D_FAM_POSPOOL_SINCOS) {
       const int F = a.C / 6;  // channel = axis*2F + t ; t<F sin, t>=F cos  (:70-83)
       const int t = c % (2 * F);
       lp.axis[i] = c / (2 * F);
       lp.is_cos[i] = t >= F;
       lp.a[i] = a.p0[t % F];
-    } else if (FAM == CL3D_FAM_ADAPTIVE_DP) {
+    } else if constexpr (FAM == CL3D_FAM_ADAPTIVE_DP) {
       const int g = c / a.shared;  // :194-197 channel c uses weight row c // S
       lp.a[i] = a.p0[g * 3 + 0];
       lp.b[i] = a.p0[g * 3 + 1];
@@ -89,19 +92,20 @@ __device__ __forceinline__ void load_lane_params(LaneParams<FAM, CI>& lp, const 
   }
 }
 
-// weight of channel slot i for relative position dp (float4: x,y,z,scale)
+// weight of channel slot i for relative position dp (float4: x,y,z,-)
 template <int FAM, int CI>
 __device__ __forceinline__ float family_weight(const LaneParams<FAM, CI>& lp, int i, const float4& dp) {
-  if (FAM == CL3D_FAM_POSPOOL_XYZ) {
+  if constexpr (FAM == CL3D_FAM_POSPOOL_XYZ) {
     return lp.axis[i] == 0 ? dp.x : (lp.axis[i] == 1 ? dp.y : dp.z);
-  } else if (FAM == CL3D_FAM_POSPOOL_SINCOS) {
+  } else if constexpr (FAM == CL3D_FAM_POSPOOL_SINCOS) {
     const float p = lp.axis[i] == 0 ? dp.x : (lp.axis[i] == 1 ? dp.y : dp.z);
     const float arg = __fdiv_rn(__fmul_rn(100.f, p), lp.a[i]);  // torch.div(alpha * dp, dim_mat) :75-77
     return lp.is_cos[i] ? cosf(arg) : sinf(arg);
-  } else if (FAM == CL3D_FAM_ADAPTIVE_DP) {
+  } else if constexpr (FAM == CL3D_FAM_ADAPTIVE_DP) {
     return fmaf(lp.c[i], dp.z, fmaf(lp.b[i], dp.y, fmaf(lp.a[i], dp.x, lp.d[i])));  // 1x1 conv 3 -> C/S, bias
+  } else {
+    return 0.f;
   }
-  return 0.f;
 }
 
 // PseudoGrid influence of kernel point kp on relative position dp (:385-403), mask applied by caller
@@ -114,32 +118,105 @@ __device__ __forceinline__ float pg_influence(float dx, float dy, float dz, cons
   return h > 0.f ? h : 0.f;
 }
 
-// shared-memory carve-up (per CTA)
+template <int FAM>
+constexpr int rows_in_flight() {  // independent row loads per lane before they are consumed
+  return (FAM == CL3D_FAM_PSEUDOGRID || FAM == CL3D_FAM_POSPOOL_SINCOS) ? 2 : 4;
+}
+template <int FAM, bool BWD>
+constexpr int num_acc() {
+  return FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : ((BWD && FAM == CL3D_FAM_ADAPTIVE_DP) ? 4 : 1);
+}
+
+// shared-memory carve-up (per CTA): per-warp slot arrays (dp + row index, influences / scales) + output tile
 struct SmemLayout {
-  size_t stage_off, dp_off, idx_off, h_off, out_off, bar_off, red_off, total;
+  size_t dp_off, h_off, out_off, red_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K_or_rows, int chunkC, bool pseudogrid, int red_floats) {
+__host__ __device__ inline SmemLayout smem_layout(int chunkC, int red_floats) {
   SmemLayout L;
   size_t o = 0;
-  L.stage_off = o;
-  o += (size_t)kAggWarps * kStageBytes;
   L.dp_off = o;
-  o += (size_t)kAggWarps * K_or_rows * sizeof(float4);
-  L.idx_off = o;
-  o += (size_t)kAggWarps * K_or_rows * sizeof(int);
-  o = align_up(o, 16);
+  o += (size_t)kAggWarps * kSlots * sizeof(float4);
   L.h_off = o;
-  o += pseudogrid ? (size_t)kAggWarps * K_or_rows * kMaxKP * sizeof(float) : 0;
+  o += (size_t)kAggWarps * kSlots * kMaxKP * sizeof(float);
   L.out_off = o;
   o += (size_t)chunkC * (kTile + 1) * sizeof(float);
   o = align_up(o, 16);
   L.red_off = o;
   o += (size_t)red_floats * sizeof(float);
-  o = align_up(o, 16);
-  L.bar_off = o;
-  o += (size_t)kAggWarps * sizeof(uint64_t);
-  L.total = o;
+  L.total = align_up(o, 16);
   return L;
+}
+
+// one staged slot: applies the family to the row values v[CI] of that slot
+template <int FAM, int CI, bool BWD, int NACC>
+__device__ __forceinline__ void apply_slot(const float (&v)[CI], const float4& dp, const float* __restrict__ hk,
+                                           const LaneParams<FAM, CI>& lp, float (&acc)[NACC][CI]) {
+  if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
+    const float4* h4 = reinterpret_cast<const float4*>(hk);  // 16 influences of this slot (0 beyond nkp)
+#pragma unroll
+    for (int k4 = 0; k4 < kMaxKP / 4; ++k4) {
+      const float4 h = h4[k4];
+#pragma unroll
+      for (int i = 0; i < CI; ++i) {
+        acc[k4 * 4 + 0][i] = fmaf(h.x, v[i], acc[k4 * 4 + 0][i]);
+        acc[k4 * 4 + 1][i] = fmaf(h.y, v[i], acc[k4 * 4 + 1][i]);
+        acc[k4 * 4 + 2][i] = fmaf(h.z, v[i], acc[k4 * 4 + 2][i]);
+        acc[k4 * 4 + 3][i] = fmaf(h.w, v[i], acc[k4 * 4 + 3][i]);
+      }
+    }
+  } else if constexpr (BWD && FAM == CL3D_FAM_ADAPTIVE_DP) {
+    const float sc = hk[0];  // 1/ncount (avg) or 1
+#pragma unroll
+    for (int i = 0; i < CI; ++i) {
+      const float gs = v[i] * sc;
+      acc[0][i] = fmaf(gs, dp.x, acc[0][i]);  // S_x, S_y, S_z, S_1
+      acc[1][i] = fmaf(gs, dp.y, acc[1][i]);
+      acc[2][i] = fmaf(gs, dp.z, acc[2][i]);
+      acc[3][i] += gs;
+    }
+  } else if constexpr (BWD) {
+    const float sc = hk[0];
+#pragma unroll
+    for (int i = 0; i < CI; ++i) acc[0][i] = fmaf(v[i] * sc, family_weight<FAM, CI>(lp, i, dp), acc[0][i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CI; ++i) acc[0][i] = fmaf(v[i], family_weight<FAM, CI>(lp, i, dp), acc[0][i]);
+  }
+}
+
+// Consume n staged slots.  dp.w holds the row's ELEMENT OFFSET (row index * Cp) as a 32-bit unsigned, `lbase`
+// is the per-lane base pointer (matrix + chunk offset + lane): one IMAD.WIDE per row, then the CI loads use
+// immediate offsets (+32 floats each).  Lanes past the chunk read whatever follows (the next row, or the
+// CL3D_PM_SLACK floats every point-major buffer carries after its last row); their results are never stored.
+// Rows are loaded U at a time straight into registers (U*CI independent loads in flight per lane).
+template <int FAM, int CI, bool BWD, int NACC>
+__device__ __forceinline__ void consume_slots(const float* __restrict__ lbase,
+                                              const float4* __restrict__ s_dp, const float* __restrict__ s_h, int n,
+                                              const LaneParams<FAM, CI>& lp, float (&acc)[NACC][CI]) {
+  constexpr int U = rows_in_flight<FAM>();
+  constexpr int HS = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;  // floats of s_h per slot
+  int s = 0;
+  for (; s + U <= n; s += U) {
+    float4 dp[U];
+    float v[U][CI];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dp[u] = s_dp[s + u];
+      const float* row = lbase + __float_as_uint(dp[u].w);
+#pragma unroll
+      for (int i = 0; i < CI; ++i) v[u][i] = __ldg(row + 32 * i);  // lanes past the chunk read slack (unused)
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) apply_slot<FAM, CI, BWD, NACC>(v[u], dp[u], s_h + (size_t)(s + u) * HS, lp, acc);
+  }
+  for (; s < n; ++s) {
+    const float4 dp = s_dp[s];
+    const float* row = lbase + __float_as_uint(dp.w);
+    float v[CI];
+#pragma unroll
+    for (int i = 0; i < CI; ++i) v[i] = __ldg(row + 32 * i);
+    apply_slot<FAM, CI, BWD, NACC>(v, dp, s_h + (size_t)s * HS, lp, acc);
+  }
 }
 
 // =================================================================================================
@@ -151,41 +228,28 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_fwd_kernel(const AggArgs a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * 32 * CI;
   const int chunkC = min(32 * CI, a.Cp - c0);  // multiple of 8
-  const uint32_t row_bytes = (uint32_t)chunkC * 4u;
-  const SmemLayout L = smem_layout(a.K, 32 * CI, FAM == CL3D_FAM_PSEUDOGRID, 0);
-  float* s_stage = reinterpret_cast<float*>(smem + L.stage_off + (size_t)warp * kStageBytes);
-  float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * a.K;
-  int* s_idx = reinterpret_cast<int*>(smem + L.idx_off) + (size_t)warp * a.K;
-  float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * a.K * kMaxKP;
+  const SmemLayout L = smem_layout(32 * CI, 0);
+  float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
+  float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * kSlots * kMaxKP;
   float* s_out = reinterpret_cast<float*>(smem + L.out_off);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off) + warp;
 
   const int tiles_per_cloud = (a.M + kTile - 1) / kTile;
   const int b = blockIdx.x / tiles_per_cloud;
   const int q0 = (blockIdx.x % tiles_per_cloud) * kTile;
 
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
-  uint32_t phase = 0;
-
   LaneParams<FAM, CI> lp;
   load_lane_params<FAM, CI>(lp, a, c0, lane);
-  // PseudoGrid: kernel weights of my channels stay in registers, kernel points in smem via s_h prologue
-  float wk[FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1][CI];
-  if (FAM == CL3D_FAM_PSEUDOGRID) {
+  constexpr int NACC = num_acc<FAM, false>();
+  constexpr int NWK = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;
+  float wk[NWK][CI];
 #pragma unroll
-    for (int kp = 0; kp < kMaxKP; ++kp)
+  for (int kp = 0; kp < NWK; ++kp)
 #pragma unroll
-      for (int i = 0; i < CI; ++i) {
-        const int c = c0 + lane + 32 * i;
-        wk[kp][i] = (kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
-      }
-  }
-
-  const float* feat = a.feat_pm + (size_t)b * a.N * a.Cp + c0;
+    for (int i = 0; i < CI; ++i) {
+      const int c = c0 + lane + 32 * i;
+      wk[kp][i] = (FAM == CL3D_FAM_PSEUDOGRID && kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
+    }
+  const float* feat = a.feat_pm + (size_t)b * a.N * a.Cp + c0 + lane;  // per-lane base pointer
   const float* sxyz = a.support_xyz + (size_t)b * a.N * 3;
 
   for (int ql = warp; ql < kTile; ql += kAggWarps) {
@@ -197,73 +261,40 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_fwd_kernel(const AggArgs a
       const size_t gq = (size_t)b * a.M + q;
       const int nrows = a.ncount[gq];
       const float qx = a.query_xyz[gq * 3 + 0], qy = a.query_xyz[gq * 3 + 1], qz = a.query_xyz[gq * 3 + 2];
-      // ---- prologue: indices, relative positions (pt_utils.py:127-129), PseudoGrid influences
-      for (int k = lane; k < nrows; k += 32) {
-        const int j = a.idx[gq * a.K + k];
-        s_idx[k] = j;
-        float dx = __fsub_rn(sxyz[j * 3 + 0], qx), dy = __fsub_rn(sxyz[j * 3 + 1], qy),
-              dz = __fsub_rn(sxyz[j * 3 + 2], qz);
-        if (a.normalize) {  // torch's CUDA `tensor /= python_scalar` multiplies by the fp32 reciprocal
-          dx = __fmul_rn(dx, a.inv_radius);
-          dy = __fmul_rn(dy, a.inv_radius);
-          dz = __fmul_rn(dz, a.inv_radius);
-        }
-        s_dp[k] = make_float4(dx, dy, dz, 0.f);
-        if (FAM == CL3D_FAM_PSEUDOGRID) {
-          for (int kp = 0; kp < a.nkp; ++kp)
-            s_h[k * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
-          for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[k * kMaxKP + kp] = 0.f;
-        }
-      }
-      __syncwarp();
-      float acc[FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1][CI];
+      float acc[NACC][CI];
 #pragma unroll
-      for (int kp = 0; kp < (FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1); ++kp)
+      for (int s = 0; s < NACC; ++s)
 #pragma unroll
-        for (int i = 0; i < CI; ++i) acc[kp][i] = 0.f;
-
-      for (int k0 = 0; k0 < nrows; k0 += a.rows_per_stage) {
-        const int rows = min(a.rows_per_stage, nrows - k0);
-        // ---- stage `rows` neighbour rows through TMA bulk copies (one per lane)
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * row_bytes);
-        __syncwarp();
-        for (int kk = lane; kk < rows; kk += 32)
-          bulk_g2s(s_stage + (size_t)kk * chunkC, feat + (size_t)s_idx[k0 + kk] * a.Cp, row_bytes, bar);
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        // ---- transform + reduce over the staged rows
-        for (int kk = 0; kk < rows; ++kk) {
-          const float4 dp = s_dp[k0 + kk];
-          const float* row = s_stage + (size_t)kk * chunkC;
-          if (FAM == CL3D_FAM_PSEUDOGRID) {
-            float v[CI];
-#pragma unroll
-            for (int i = 0; i < CI; ++i) v[i] = (lane + 32 * i < chunkC) ? row[lane + 32 * i] : 0.f;
-            const float* hk = s_h + (size_t)(k0 + kk) * kMaxKP;
-#pragma unroll
-            for (int kp = 0; kp < kMaxKP; ++kp) {
-              const float h = hk[kp];  // entries >= nkp are never read as non-zero: wk is 0 there
-#pragma unroll
-              for (int i = 0; i < CI; ++i) acc[kp][i] = fmaf(h, v[i], acc[kp][i]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < CI; ++i) {
-              if (lane + 32 * i < chunkC) {
-                const float w = family_weight<FAM, CI>(lp, i, dp);
-                acc[0][i] = fmaf(row[lane + 32 * i], w, acc[0][i]);
-              }
-            }
+        for (int i = 0; i < CI; ++i) acc[s][i] = 0.f;
+      for (int k0 = 0; k0 < nrows; k0 += kSlots) {
+        const int rows = min(kSlots, nrows - k0);
+        // ---- stage: indices, relative positions (pt_utils.py:127-129), PseudoGrid influences
+        if (lane < rows) {
+          const int j = a.idx[gq * a.K + k0 + lane];
+          float dx = __fsub_rn(sxyz[j * 3 + 0], qx), dy = __fsub_rn(sxyz[j * 3 + 1], qy),
+                dz = __fsub_rn(sxyz[j * 3 + 2], qz);
+          if (a.normalize) {  // torch's CUDA `tensor /= python_scalar` multiplies by the fp32 reciprocal
+            dx = __fmul_rn(dx, a.inv_radius);
+            dy = __fmul_rn(dy, a.inv_radius);
+            dz = __fmul_rn(dz, a.inv_radius);
+          }
+          s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)j * (unsigned)a.Cp));
+          if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
+            for (int kp = 0; kp < a.nkp; ++kp)
+              s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
+            for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[lane * kMaxKP + kp] = 0.f;
           }
         }
-        __syncwarp();  // all lanes done reading the stage before it is refilled
+        __syncwarp();
+        consume_slots<FAM, CI, false, NACC>(feat, s_dp, s_h, rows, lp, acc);
+        __syncwarp();  // slots are rewritten by the next round / query
       }
-      if (FAM == CL3D_FAM_PSEUDOGRID) {
+      if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
 #pragma unroll
         for (int i = 0; i < CI; ++i) {
           float r = 0.f;
 #pragma unroll
-          for (int kp = 0; kp < kMaxKP; ++kp) r = fmaf(acc[kp][i], wk[kp][i], r);  // sum_k' Wk[k',c] * t[k',c]  :418-419
+          for (int kp = 0; kp < kMaxKP; ++kp) r = fmaf(acc[kp][i], wk[kp][i], r);  // sum_k' Wk[k',c] t[k',c]  :418-419
           res[i] = r;
         }
       } else {
@@ -310,42 +341,35 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * 32 * CI;
   const int chunkC = min(32 * CI, a.Cp - c0);
-  const uint32_t row_bytes = (uint32_t)chunkC * 4u;
-  constexpr int NACC = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : (FAM == CL3D_FAM_ADAPTIVE_DP ? 4 : 1);
+  constexpr int NACC = num_acc<FAM, true>();
+  constexpr bool HASP = FAM == CL3D_FAM_ADAPTIVE_DP || FAM == CL3D_FAM_PSEUDOGRID;
+  constexpr int HS = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;
   const int ppc = params_per_channel<FAM>(a.nkp);
-  const int R = a.rows_per_stage;
-  const SmemLayout L = smem_layout(R, 32 * CI, FAM == CL3D_FAM_PSEUDOGRID, ppc * 32 * CI);
-  float* s_stage = reinterpret_cast<float*>(smem + L.stage_off + (size_t)warp * kStageBytes);
-  float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * R;
-  int* s_q = reinterpret_cast<int*>(smem + L.idx_off) + (size_t)warp * R;
-  float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * R * kMaxKP;
+  const SmemLayout L = smem_layout(32 * CI, ppc * 32 * CI);
+  float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
+  float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * kSlots * kMaxKP;
   float* s_out = reinterpret_cast<float*>(smem + L.out_off);
   float* s_red = reinterpret_cast<float*>(smem + L.red_off);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off) + warp;
-
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
-  uint32_t phase = 0;
 
   LaneParams<FAM, CI> lp;
   load_lane_params<FAM, CI>(lp, a, c0, lane);
-  float wk[FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1][CI];
-  if (FAM == CL3D_FAM_PSEUDOGRID) {
+  bool ok[CI];
 #pragma unroll
-    for (int kp = 0; kp < kMaxKP; ++kp)
+  for (int i = 0; i < CI; ++i) ok[i] = lane + 32 * i < chunkC;
+  constexpr int NWK = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;
+  float wk[NWK][CI];
 #pragma unroll
-      for (int i = 0; i < CI; ++i) {
-        const int c = c0 + lane + 32 * i;
-        wk[kp][i] = (kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
-      }
-  }
+  for (int kp = 0; kp < NWK; ++kp)
+#pragma unroll
+    for (int i = 0; i < CI; ++i) {
+      const int c = c0 + lane + 32 * i;
+      wk[kp][i] = (FAM == CL3D_FAM_PSEUDOGRID && kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
+    }
   // per-lane parameter-gradient accumulators over all points this warp handles
-  float pacc[(FAM == CL3D_FAM_ADAPTIVE_DP || FAM == CL3D_FAM_PSEUDOGRID) ? NACC : 1][CI];
+  constexpr int NP = HASP ? NACC : 1;
+  float pacc[NP][CI];
 #pragma unroll
-  for (int s = 0; s < ((FAM == CL3D_FAM_ADAPTIVE_DP || FAM == CL3D_FAM_PSEUDOGRID) ? NACC : 1); ++s)
+  for (int s = 0; s < NP; ++s)
 #pragma unroll
     for (int i = 0; i < CI; ++i) pacc[s][i] = 0.f;
 
@@ -353,7 +377,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int b = tile / tiles_per_cloud;
     const int j0 = (tile % tiles_per_cloud) * kTile;
-    const float* gpm = a.g_pm + (size_t)b * a.M * a.Cp + c0;
+    const float* gpm = a.g_pm + (size_t)b * a.M * a.Cp + c0 + lane;  // per-lane base pointer
     const float* qxyz = a.query_xyz + (size_t)b * a.M * 3;
     const int* ncnt = a.ncount + (size_t)b * a.M;
     const int* off = a.csr_off + (size_t)b * (a.N + 1);
@@ -374,12 +398,10 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
 #pragma unroll
           for (int i = 0; i < CI; ++i) acc[s][i] = 0.f;
 
-        for (int eb = e0; eb < e1; eb += R) {
-          const int rows = min(R, e1 - eb);
-          for (int r = lane; r < rows; r += 32) {
-            const int code = ent[eb + r];
-            const int q = code / a.K;
-            s_q[r] = q;
+        for (int eb = e0; eb < e1; eb += kSlots) {
+          const int rows = min(kSlots, e1 - eb);
+          if (lane < rows) {
+            const int q = ent[eb + lane] / a.K;
             float dx = __fsub_rn(px, qxyz[q * 3 + 0]), dy = __fsub_rn(py, qxyz[q * 3 + 1]),
                   dz = __fsub_rn(pz, qxyz[q * 3 + 2]);
             if (a.normalize) {
@@ -387,60 +409,26 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
               dy = __fmul_rn(dy, a.inv_radius);
               dz = __fmul_rn(dz, a.inv_radius);
             }
-            const float scale = a.reduction == CL3D_REDUCE_AVG ? __fdiv_rn(1.f, (float)ncnt[q]) : 1.f;
-            s_dp[r] = make_float4(dx, dy, dz, scale);
-            if (FAM == CL3D_FAM_PSEUDOGRID) {
+            s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)q * (unsigned)a.Cp));
+            if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
               for (int kp = 0; kp < a.nkp; ++kp)
-                s_h[r * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
-              for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[r * kMaxKP + kp] = 0.f;
-            }
-          }
-          if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * row_bytes);
-          __syncwarp();
-          for (int r = lane; r < rows; r += 32)
-            bulk_g2s(s_stage + (size_t)r * chunkC, gpm + (size_t)s_q[r] * a.Cp, row_bytes, bar);
-          mbar_wait(bar, phase);
-          phase ^= 1u;
-          for (int r = 0; r < rows; ++r) {
-            const float4 dp = s_dp[r];
-            const float* row = s_stage + (size_t)r * chunkC;
-            if (FAM == CL3D_FAM_PSEUDOGRID) {
-              float v[CI];
-#pragma unroll
-              for (int i = 0; i < CI; ++i) v[i] = (lane + 32 * i < chunkC) ? row[lane + 32 * i] : 0.f;
-              const float* hk = s_h + (size_t)r * kMaxKP;
-#pragma unroll
-              for (int kp = 0; kp < kMaxKP; ++kp) {
-                const float h = hk[kp];
-#pragma unroll
-                for (int i = 0; i < CI; ++i) acc[kp][i] = fmaf(h, v[i], acc[kp][i]);
-              }
+                s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
+              for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[lane * kMaxKP + kp] = 0.f;
             } else {
-#pragma unroll
-              for (int i = 0; i < CI; ++i) {
-                if (lane + 32 * i < chunkC) {
-                  const float gs = row[lane + 32 * i] * dp.w;
-                  if (FAM == CL3D_FAM_ADAPTIVE_DP) {  // S_x, S_y, S_z, S_1
-                    acc[0][i] = fmaf(gs, dp.x, acc[0][i]);
-                    acc[1][i] = fmaf(gs, dp.y, acc[1][i]);
-                    acc[2][i] = fmaf(gs, dp.z, acc[2][i]);
-                    acc[3][i] += gs;
-                  } else {
-                    acc[0][i] = fmaf(gs, family_weight<FAM, CI>(lp, i, dp), acc[0][i]);
-                  }
-                }
-              }
+              s_h[lane * HS] = a.reduction == CL3D_REDUCE_AVG ? __fdiv_rn(1.f, (float)ncnt[q]) : 1.f;
             }
           }
+          __syncwarp();
+          consume_slots<FAM, CI, true, NACC>(gpm, s_dp, s_h, rows, lp, acc);
           __syncwarp();
         }
         // ---- epilogue: gradient w.r.t. this support point's features, parameter gradients
-        if (FAM == CL3D_FAM_ADAPTIVE_DP || FAM == CL3D_FAM_PSEUDOGRID) {
-          const float* frow = a.feat_pm + ((size_t)b * a.N + j) * a.Cp + c0;
+        if constexpr (HASP) {
+          const float* frow = a.feat_pm + ((size_t)b * a.N + j) * a.Cp + c0 + lane;
 #pragma unroll
           for (int i = 0; i < CI; ++i) {
-            const float f = (lane + 32 * i < chunkC) ? frow[lane + 32 * i] : 0.f;
-            if (FAM == CL3D_FAM_ADAPTIVE_DP) {
+            const float f = ok[i] ? __ldg(frow + 32 * i) : 0.f;
+            if constexpr (FAM == CL3D_FAM_ADAPTIVE_DP) {
               res[i] = fmaf(lp.c[i], acc[2][i], fmaf(lp.b[i], acc[1][i], fmaf(lp.a[i], acc[0][i], lp.d[i] * acc[3][i])));
 #pragma unroll
               for (int s = 0; s < 4; ++s) pacc[s][i] = fmaf(f, acc[s][i], pacc[s][i]);
@@ -472,19 +460,19 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
     __syncthreads();
   }
   // ---- CTA-level reduction of the parameter-gradient accumulators (warps take turns: fixed order)
-  if (FAM == CL3D_FAM_ADAPTIVE_DP || FAM == CL3D_FAM_PSEUDOGRID) {
+  if constexpr (HASP) {
     for (int w = 0; w < kAggWarps; ++w) {
       if (warp == w) {
-        for (int s = 0; s < ppc; ++s)
 #pragma unroll
-          for (int i = 0; i < CI; ++i) {
-            float* p = s_red + (size_t)s * 32 * CI + lane + 32 * i;
-            // pacc is indexed with a runtime s only through this unrolled select
-            float v = 0.f;
+        for (int s = 0; s < NP; ++s) {
+          if (s < ppc) {
 #pragma unroll
-            for (int ss = 0; ss < NACC; ++ss) v = (ss == s) ? pacc[ss][i] : v;
-            *p = (w == 0) ? v : (*p + v);
+            for (int i = 0; i < CI; ++i) {
+              float* p = s_red + (size_t)s * 32 * CI + lane + 32 * i;
+              *p = (w == 0) ? pacc[s][i] : (*p + pacc[s][i]);
+            }
           }
+        }
       }
       __syncthreads();
     }
@@ -503,10 +491,12 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
 template <int FAM, int CI>
 static int launch_fwd(const AggArgs& a, cudaStream_t stream) {
   const int nchunks = ceil_div(a.Cp, 32 * CI);
-  const SmemLayout L = smem_layout(a.K, 32 * CI, FAM == CL3D_FAM_PSEUDOGRID, 0);
-  cudaFuncSetAttribute(agg_fwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  const SmemLayout L = smem_layout(32 * CI, 0);
+  if (L.total > 48 * 1024)
+    cudaFuncSetAttribute(agg_fwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   dim3 grid(a.ntiles, nchunks);
-  agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a); CL3D_LAUNCHED(1);
+  agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  CL3D_LAUNCHED(1);
   return check_launch("agg_fwd_kernel");
 }
 
@@ -514,10 +504,12 @@ template <int FAM, int CI>
 static int launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   const int nchunks = ceil_div(a.Cp, 32 * CI);
   const int ppc = params_per_channel<FAM>(a.nkp);
-  const SmemLayout L = smem_layout(a.rows_per_stage, 32 * CI, FAM == CL3D_FAM_PSEUDOGRID, ppc * 32 * CI);
-  cudaFuncSetAttribute(agg_bwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  const SmemLayout L = smem_layout(32 * CI, ppc * 32 * CI);
+  if (L.total > 48 * 1024)
+    cudaFuncSetAttribute(agg_bwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   dim3 grid(grid_x, nchunks);
-  agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a); CL3D_LAUNCHED(1);
+  agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  CL3D_LAUNCHED(1);
   return check_launch("agg_bwd_kernel");
 }
 
@@ -536,13 +528,19 @@ static int pick_ci(int family, int Cp) {
     case 5: return FN<FAM, 5>(__VA_ARGS__);                \
     default: return FN<FAM, 6>(__VA_ARGS__);               \
   }
+#define DISPATCH_CI3(FN, FAM, ...)                         \
+  switch (ci) {                                            \
+    case 1: return FN<FAM, 1>(__VA_ARGS__);                \
+    case 2: return FN<FAM, 2>(__VA_ARGS__);                \
+    default: return FN<FAM, 3>(__VA_ARGS__);               \
+  }
 
 static int dispatch_fwd(int family, int ci, const AggArgs& a, cudaStream_t s) {
   switch (family) {
     case CL3D_FAM_POSPOOL_XYZ: DISPATCH_CI(launch_fwd, CL3D_FAM_POSPOOL_XYZ, a, s)
     case CL3D_FAM_POSPOOL_SINCOS: DISPATCH_CI(launch_fwd, CL3D_FAM_POSPOOL_SINCOS, a, s)
     case CL3D_FAM_ADAPTIVE_DP: DISPATCH_CI(launch_fwd, CL3D_FAM_ADAPTIVE_DP, a, s)
-    case CL3D_FAM_PSEUDOGRID: DISPATCH_CI(launch_fwd, CL3D_FAM_PSEUDOGRID, a, s)
+    case CL3D_FAM_PSEUDOGRID: DISPATCH_CI3(launch_fwd, CL3D_FAM_PSEUDOGRID, a, s)
   }
   return CL3D_ERR_UNSUPPORTED;
 }
@@ -551,13 +549,13 @@ static int dispatch_bwd(int family, int ci, const AggArgs& a, int gx, cudaStream
     case CL3D_FAM_POSPOOL_XYZ: DISPATCH_CI(launch_bwd, CL3D_FAM_POSPOOL_XYZ, a, gx, s)
     case CL3D_FAM_POSPOOL_SINCOS: DISPATCH_CI(launch_bwd, CL3D_FAM_POSPOOL_SINCOS, a, gx, s)
     case CL3D_FAM_ADAPTIVE_DP: DISPATCH_CI(launch_bwd, CL3D_FAM_ADAPTIVE_DP, a, gx, s)
-    case CL3D_FAM_PSEUDOGRID: DISPATCH_CI(launch_bwd, CL3D_FAM_PSEUDOGRID, a, gx, s)
+    case CL3D_FAM_PSEUDOGRID: DISPATCH_CI3(launch_bwd, CL3D_FAM_PSEUDOGRID, a, gx, s)
   }
   return CL3D_ERR_UNSUPPORTED;
 }
 
 static int bwd_grid_x(int ntiles) {
-  const int cap = sm_count() * 2;
+  const int cap = sm_count() * 4;
   return ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap;
 }
 
@@ -588,6 +586,19 @@ static int check_common(int family, int reduction, int B, int N, int M, int K, i
   return CL3D_OK;
 }
 
+static void fill_common(AggArgs& a, int B, int N, int M, int K, int C, float radius, int reduction, int normalize,
+                        int shared, int nkp, float extent, int influence) {
+  a.B = B; a.N = N; a.M = M; a.K = K; a.C = C;
+  a.Cp = padded_channels(C);
+  a.reduction = reduction;
+  a.normalize = normalize;
+  a.shared = shared > 0 ? shared : 1;
+  a.nkp = nkp;
+  a.influence = influence;
+  a.inv_radius = 1.0f / radius;
+  a.extent = extent;
+}
+
 extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, const float* query_xyz,
                             const float* support_xyz, const int* idx, const int* ncount, const float* p0,
                             const float* p1, int B, int N, int M, int K, int C, float radius, int normalize,
@@ -607,21 +618,9 @@ extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, con
   a.p1 = p1;
   a.out = agg;
   a.partial = bn_partial;
-  a.B = B; a.N = N; a.M = M; a.K = K; a.C = C;
-  a.Cp = padded_channels(C);
-  a.reduction = reduction;
-  a.normalize = normalize;
-  a.shared = shared > 0 ? shared : 1;
-  a.nkp = nkp;
-  a.influence = influence;
-  a.inv_radius = 1.0f / radius;
-  a.extent = extent;
+  fill_common(a, B, N, M, K, C, radius, reduction, normalize, shared, nkp, extent, influence);
   a.ntiles = B * ceil_div(M, kTile);
-  const int ci = pick_ci(family, a.Cp);
-  const int chunk = 32 * ci < a.Cp ? 32 * ci : a.Cp;
-  a.rows_per_stage = kStageBytes / (chunk * 4);
-  if (a.rows_per_stage > K) a.rows_per_stage = K;
-  return dispatch_fwd(family, ci, a, (cudaStream_t)stream_);
+  return dispatch_fwd(family, pick_ci(family, a.Cp), a, (cudaStream_t)stream_);
 }
 
 extern "C" int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const float* feat_pm,
@@ -648,19 +647,7 @@ extern "C" int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const 
   a.p1 = p1;
   a.out = grad_feat;
   a.partial = grad_params_partial;
-  a.B = B; a.N = N; a.M = M; a.K = K; a.C = C;
-  a.Cp = padded_channels(C);
-  a.reduction = reduction;
-  a.normalize = normalize;
-  a.shared = shared > 0 ? shared : 1;
-  a.nkp = nkp;
-  a.influence = influence;
-  a.inv_radius = 1.0f / radius;
-  a.extent = extent;
+  fill_common(a, B, N, M, K, C, radius, reduction, normalize, shared, nkp, extent, influence);
   a.ntiles = B * ceil_div(N, kTile);
-  const int ci = pick_ci(family, a.Cp);
-  const int chunk = 32 * ci < a.Cp ? 32 * ci : a.Cp;
-  a.rows_per_stage = kStageBytes / (chunk * 4);
-  if (a.rows_per_stage > 64) a.rows_per_stage = 64;
-  return dispatch_bwd(family, ci, a, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);
+  return dispatch_bwd(family, pick_ci(family, a.Cp), a, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);
 }

@@ -24,10 +24,24 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   const int c = blockIdx.x * 32 + tx;
   double a1 = 0.0, a2 = 0.0;
   if (training && c < C) {
-    for (int t = ty; t < ntiles; t += 32) {
+    double b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
+    int t = ty;
+    for (; t + 96 < ntiles; t += 128) {  // four independent load streams per thread
+      a1 += (double)partial[((size_t)t * 2 + 0) * C + c];
+      a2 += (double)partial[((size_t)t * 2 + 1) * C + c];
+      b1 += (double)partial[((size_t)(t + 32) * 2 + 0) * C + c];
+      b2 += (double)partial[((size_t)(t + 32) * 2 + 1) * C + c];
+      c1 += (double)partial[((size_t)(t + 64) * 2 + 0) * C + c];
+      c2 += (double)partial[((size_t)(t + 64) * 2 + 1) * C + c];
+      d1 += (double)partial[((size_t)(t + 96) * 2 + 0) * C + c];
+      d2 += (double)partial[((size_t)(t + 96) * 2 + 1) * C + c];
+    }
+    for (; t < ntiles; t += 32) {
       a1 += (double)partial[((size_t)t * 2 + 0) * C + c];
       a2 += (double)partial[((size_t)t * 2 + 1) * C + c];
     }
+    a1 = (a1 + b1) + (c1 + d1);
+    a2 = (a2 + b2) + (c2 + d2);
   }
   s1[ty][tx] = a1;
   s2[ty][tx] = a2;
@@ -151,11 +165,26 @@ __global__ void __launch_bounds__(1024) bn_reduce2_kernel(const float* __restric
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   double a1 = 0.0, a2 = 0.0;
-  if (c < C)
-    for (int t = ty; t < ntiles; t += 32) {
+  if (c < C) {
+    double b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
+    int t = ty;
+    for (; t + 96 < ntiles; t += 128) {
+      a1 += (double)partial[((size_t)t * 2 + 0) * C + c];
+      a2 += (double)partial[((size_t)t * 2 + 1) * C + c];
+      b1 += (double)partial[((size_t)(t + 32) * 2 + 0) * C + c];
+      b2 += (double)partial[((size_t)(t + 32) * 2 + 1) * C + c];
+      c1 += (double)partial[((size_t)(t + 64) * 2 + 0) * C + c];
+      c2 += (double)partial[((size_t)(t + 64) * 2 + 1) * C + c];
+      d1 += (double)partial[((size_t)(t + 96) * 2 + 0) * C + c];
+      d2 += (double)partial[((size_t)(t + 96) * 2 + 1) * C + c];
+    }
+    for (; t < ntiles; t += 32) {
       a1 += (double)partial[((size_t)t * 2 + 0) * C + c];
       a2 += (double)partial[((size_t)t * 2 + 1) * C + c];
     }
+    a1 = (a1 + b1) + (c1 + d1);
+    a2 = (a2 + b2) + (c2 + d2);
+  }
   s1[ty][tx] = a1;
   s2[ty][tx] = a2;
   __syncthreads();

@@ -120,8 +120,18 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + tx;
   double acc = 0.0;
-  if (p < P)
-    for (int t = ty; t < ntiles; t += 32) acc += (double)partial[(size_t)t * P + p];
+  if (p < P) {
+    double b = 0.0, c = 0.0, d = 0.0;
+    int t = ty;
+    for (; t + 96 < ntiles; t += 128) {  // four independent load streams per thread
+      acc += (double)partial[(size_t)t * P + p];
+      b += (double)partial[(size_t)(t + 32) * P + p];
+      c += (double)partial[(size_t)(t + 64) * P + p];
+      d += (double)partial[(size_t)(t + 96) * P + p];
+    }
+    for (; t < ntiles; t += 32) acc += (double)partial[(size_t)t * P + p];
+    acc = (acc + b) + (c + d);
+  }
   s_acc[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && p < P) {

@@ -2,70 +2,99 @@
 //
 // Used for the per-point products of the fused PointWiseMLP (see pwmlp.cu): the reference's per-neighbour
 // 1x1 conv over [dp; f_i; f_j - f_i] (/root/reference/pytorch/models/local_aggregation_operators.py:254-257,
-// 288-295) is refactored into  A = f (Wc - Wr)^T  and  Bv = f Wr^T  per POINT, i.e. (B*N x C) x (C x 2*Cout)
-// products: K*C is far too small to fill a tcgen05 tile and TF32/BF16 operands would break the fp32 1e-5
-// parity bar, so these stay vectorised fp32 FMA (BASELINE.json north_star).
+// 288-295) becomes ONE per-point product (B*N x (C+3)) x ((C+3) x 2*Cout), plus its two gradients.  These are
+// skinny problems (N, K ~ 75..150): far too small to fill a tcgen05 tile, and TF32/BF16 operands would break
+// the fp32 1e-5 parity bar, so they stay vectorised fp32 FMA (BASELINE.json north_star).
 //
 //   C[m][n] = sum_k A[m*sa_m + k*sa_k] * B[k*sb_k + n*sb_n]
-// 64x64 output tile, 16-deep k tiles, 256 threads, 4x4 outputs per thread.  With splitk > 1 the k range is
-// divided among gridDim.z CTAs that write partial tiles, reduced afterwards in a fixed order.
+// CTA tile 128 x (16*TN), k tile 16, 256 threads, 8 x TN outputs per thread (TN chosen from N so that skinny
+// outputs waste few columns), operands transposed into shared memory as [k][m] / [k][n] (LDS.128 for the A
+// fragment), next k tile prefetched into registers while the current one is multiplied.  With splitk > 1 the k
+// range is divided among gridDim.z CTAs that write partial tiles, reduced afterwards in a fixed order.
 #include "common.cuh"
 
 namespace cl3d {
 
-constexpr int kGM = 64, kGN = 64, kGK = 16;
+constexpr int kBM = 128, kBK = 16;
 
-__global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
-                                                            const float* __restrict__ B, long long sb_k,
-                                                            long long sb_n, int M, int N, int K, int k_per_split,
-                                                            float* __restrict__ C, long long ldc,
-                                                            float* __restrict__ partial) {
-  __shared__ float sA[kGK][kGM + 4];
-  __shared__ float sB[kGK][kGN + 4];
-  const int m0 = blockIdx.y * kGM, n0 = blockIdx.x * kGN;
+template <int TN>
+__global__ void __launch_bounds__(256) sgemm_tiled_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
+                                                          const float* __restrict__ B, long long sb_k,
+                                                          long long sb_n, int M, int N, int K, int k_per_split,
+                                                          float* __restrict__ C, long long ldc,
+                                                          float* __restrict__ partial) {
+  constexpr int BN = 16 * TN;
+  __shared__ __align__(16) float sA[kBK][kBM + 4];
+  __shared__ __align__(16) float sB[kBK][BN + 4];
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each a 4x4 block
-  float acc[4][4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool a_k_fast = (sa_k == 1), b_k_fast = (sb_k == 1);
+  float acc[8][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // loader mapping chosen at run time so that the fastest-varying thread index follows the unit stride
-  const bool a_k_fast = (sa_k == 1), b_n_fast = (sb_n == 1);
-  for (int k0 = kbeg; k0 < kend; k0 += kGK) {
-    // A tile: kGM x kGK
-    for (int e = threadIdx.x; e < kGM * kGK; e += 256) {
-      const int mm = a_k_fast ? e / kGK : e % kGM, kk = a_k_fast ? e % kGK : e / kGM;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float ra[8], rb[TN];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      const int mm = a_k_fast ? e / kBK : e % kBM, kk = a_k_fast ? e % kBK : e / kBM;
       const int m = m0 + mm, k = k0 + kk;
-      sA[kk][mm] = (m < M && k < kend) ? A[m * sa_m + k * sa_k] : 0.f;
+      ra[r] = (m < M && k < kend) ? __ldg(A + m * sa_m + k * sa_k) : 0.f;
     }
-    for (int e = threadIdx.x; e < kGN * kGK; e += 256) {
-      const int nn = b_n_fast ? e % kGN : e / kGK, kk = b_n_fast ? e / kGN : e % kGK;
+#pragma unroll
+    for (int r = 0; r < TN; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      const int nn = b_k_fast ? e / kBK : e % BN, kk = b_k_fast ? e % kBK : e / BN;
       const int n = n0 + nn, k = k0 + kk;
-      sB[kk][nn] = (n < N && k < kend) ? B[k * sb_k + n * sb_n] : 0.f;
+      rb[r] = (n < N && k < kend) ? __ldg(B + k * sb_k + n * sb_n) : 0.f;
     }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      const int mm = a_k_fast ? e / kBK : e % kBM, kk = a_k_fast ? e % kBK : e / kBM;
+      sA[kk][mm] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < TN; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      const int nn = b_k_fast ? e / kBK : e % BN, kk = b_k_fast ? e % kBK : e / BN;
+      sB[kk][nn] = rb[r];
+    }
+  };
+
+  load_tiles(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += kBK) {
+    store_tiles();
     __syncthreads();
+    if (k0 + kBK < kend) load_tiles(k0 + kBK);  // prefetch the next k tile into registers
 #pragma unroll
-    for (int kk = 0; kk < kGK; ++kk) {
-      float a[4], b[4];
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[kk][ty * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+      for (int j = 0; j < TN; ++j) b[j] = sB[kk][tx * TN + j];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
       if (n >= N) continue;
       if (partial)
         partial[(size_t)blockIdx.z * M * N + (size_t)m * N + n] = acc[i][j];
@@ -79,9 +108,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             float* __restrict__ C, long long ldc) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)M * N) return;
-  double acc = 0.0;
-  for (int s = 0; s < splits; ++s) acc += (double)partial[(size_t)s * M * N + e];
-  C[(size_t)(e / N) * ldc + (e % N)] = (float)acc;
+  const size_t stride = (size_t)M * N;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    a0 += (double)partial[(size_t)(s + 0) * stride + e];
+    a1 += (double)partial[(size_t)(s + 1) * stride + e];
+    a2 += (double)partial[(size_t)(s + 2) * stride + e];
+    a3 += (double)partial[(size_t)(s + 3) * stride + e];
+  }
+  for (; s < splits; ++s) a0 += (double)partial[(size_t)s * stride + e];
+  C[(size_t)(e / N) * ldc + (e % N)] = (float)((a0 + a1) + (a2 + a3));
+}
+
+template <int TN>
+static void launch_sgemm(dim3 grid, cudaStream_t stream, const float* a, long long sa_m, long long sa_k, const float* b,
+                         long long sb_k, long long sb_n, int M, int N, int K, int kps, float* c, long long ldc,
+                         float* partial) {
+  sgemm_tiled_kernel<TN><<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial);
+  CL3D_LAUNCHED(1);
 }
 
 }  // namespace cl3d
@@ -101,7 +146,7 @@ extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const 
   if (splitk > K) splitk = K;
   CL3D_REQUIRE(splitk <= 65535, "cl3d_sgemm: splitk too large");
   int kps = ceil_div(K, splitk);
-  kps = ceil_div(kps, kGK) * kGK;
+  kps = ceil_div(kps, kBK) * kBK;
   splitk = ceil_div(K, kps);
   float* partial = nullptr;
   if (splitk > 1) {
@@ -111,11 +156,26 @@ extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const 
     }
     partial = (float*)workspace;
   }
-  dim3 grid(ceil_div(N, kGN), ceil_div(M, kGM), splitk);
-  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); CL3D_LAUNCHED(1);
+  // columns per thread: spread N over the fewest 128-wide column tiles, then round each tile up to 16*TN
+  const int nct = ceil_div(N, 128);
+  int tn = ceil_div(ceil_div(N, nct), 16);
+  if (tn < 1) tn = 1;
+  if (tn > 8) tn = 8;
+  dim3 grid(ceil_div(N, 16 * tn), ceil_div(M, kBM), splitk);
+  switch (tn) {
+    case 1: launch_sgemm<1>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 2: launch_sgemm<2>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 3: launch_sgemm<3>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 4: launch_sgemm<4>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 5: launch_sgemm<5>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 6: launch_sgemm<6>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 7: launch_sgemm<7>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    default: launch_sgemm<8>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+  }
   if (splitk > 1) {
     const long long total = (long long)M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splitk, M, N, c, ldc); CL3D_LAUNCHED(1);
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splitk, M, N, c, ldc);
+    CL3D_LAUNCHED(1);
   }
-  return check_launch("sgemm_strided_kernel");
+  return check_launch("sgemm_tiled_kernel");
 }

@@ -13,6 +13,14 @@ def padded_channels(C):
     return (C + 7) & ~7
 
 
+PM_SLACK = 256  # CL3D_PM_SLACK: readable floats after the last row of every gathered point-major buffer
+
+
+def _empty_pm(B, N, W, device):
+    """(B,N,W) fp32 view of an allocation with PM_SLACK floats of slack behind it"""
+    return torch.empty(B * N * W + PM_SLACK, dtype=F32, device=device)[:B * N * W].view(B, N, W)
+
+
 def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_mask=True, want_ncount=True,
                algo=0):
     """-> (idx (B,M,K) i32, idx_mask (B,M,K) i32 | None, ncount (B,M) i32 | None); bit-exact with the
@@ -70,7 +78,7 @@ def to_point_major(x_cn):
     """(B,C,N) -> (B,N,Cp) zero-padded rows"""
     require_cuda(x_cn, "features", F32)
     B, C, N = x_cn.shape
-    out = torch.empty(B, N, padded_channels(C), dtype=F32, device=x_cn.device)
+    out = _empty_pm(B, N, padded_channels(C), x_cn.device)
     check(_lib.lib().cl3d_to_point_major(ptr(x_cn), B, C, N, ptr(out), stream_ptr()), "cl3d_to_point_major")
     return out
 
@@ -180,7 +188,7 @@ def bn_relu_bwd(grad_y, x, stats, gamma, beta, training):
     dev = x.device
     partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, C, dtype=F32, device=dev)
     dgb = torch.empty(2, C, dtype=F32, device=dev)
-    g_pm = torch.empty(B, M, padded_channels(C), dtype=F32, device=dev)
+    g_pm = _empty_pm(B, M, padded_channels(C), dev)
     check(L.cl3d_bn_relu_bwd(ptr(grad_y), ptr(x), ptr(stats), ptr(gamma), ptr(beta), B, C, M, int(training),
                              ptr(partial), ptr(dgb), ptr(g_pm), stream_ptr()), "cl3d_bn_relu_bwd")
     return g_pm, dgb[0], dgb[1]
@@ -195,7 +203,7 @@ def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1):
     dev = a.device
     ldc = N if ldc is None else ldc
     if out is None:
-        out = torch.empty(M, ldc, dtype=F32, device=dev)
+        out = _empty_pm(1, M, ldc, dev).view(M, ldc)
     wsb = L.cl3d_sgemm_workspace_bytes(M, N, splitk)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if splitk > 1 else None
     check(L.cl3d_sgemm(ptr(a), sa_m, sa_k, ptr(b), sb_k, sb_n, M, N, K, ptr(out), ldc, splitk, ptr(ws), wsb,
@@ -203,31 +211,43 @@ def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1):
     return out
 
 
-def pwmlp_fwd_stats(ab_pm, wp, query_xyz, support_xyz, idx, Cout, radius):
+def to_point_major_aug(x_cn, xyz, radius):
+    """(B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | xyz/r | 0], Cpa = padded(C+3)"""
+    require_cuda(x_cn, "features", F32)
+    B, C, N = x_cn.shape
+    out = torch.empty(B, N, padded_channels(C + 3), dtype=F32, device=x_cn.device)
+    check(_lib.lib().cl3d_to_point_major_aug(ptr(x_cn), ptr(xyz), B, C, N, float(radius), ptr(out), stream_ptr()),
+          "cl3d_to_point_major_aug")
+    return out
+
+
+def pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, idx, Cout, radius):
     B, N, _ = ab_pm.shape
     M, K = idx.shape[1], idx.shape[2]
     L = _lib.lib()
     dev = ab_pm.device
     Cop = padded_channels(Cout)
-    ymax = torch.empty(B, Cout, M, dtype=F32, device=dev)
-    ymin = torch.empty(B, Cout, M, dtype=F32, device=dev)
-    arg = torch.empty(B, M, Cop, dtype=torch.int16, device=dev)
+    ysel = torch.empty(B, Cout, M, dtype=F32, device=dev)
+    aq = _empty_pm(B, M, Cop, dev)
+    sq = torch.empty(B, M, Cop, dtype=F32, device=dev)
+    karg = torch.empty(B, M, Cop, dtype=torch.uint8, device=dev)
     partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, Cout, dtype=F32, device=dev)
-    check(L.cl3d_pwmlp_fwd_stats(ptr(ab_pm), ptr(wp), ptr(query_xyz), ptr(support_xyz), ptr(idx), B, N, M, K, Cout,
-                                 float(radius), ptr(ymax), ptr(ymin), ptr(arg), ptr(partial), stream_ptr()),
+    check(L.cl3d_pwmlp_fwd_stats(ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(idx), B, N, M, K, Cout,
+                                 float(radius), ptr(ysel), ptr(aq), ptr(sq), ptr(karg), ptr(partial), stream_ptr()),
           "cl3d_pwmlp_fwd_stats")
-    return ymax, ymin, arg, partial
+    return ysel, aq, sq, karg, partial
 
 
-def pwmlp_fwd_out(ymax, ymin, stats, gamma, beta):
-    B, Cout, M = ymax.shape
-    out = torch.empty_like(ymax)
-    check(_lib.lib().cl3d_pwmlp_fwd_out(ptr(ymax), ptr(ymin), ptr(stats), ptr(gamma), ptr(beta), B, M, Cout, ptr(out),
+def pwmlp_fwd_out(ysel, stats, gamma, beta):
+    B, Cout, M = ysel.shape
+    out = torch.empty_like(ysel)
+    check(_lib.lib().cl3d_pwmlp_fwd_out(ptr(ysel), ptr(stats), ptr(gamma), ptr(beta), B, M, Cout, ptr(out),
                                         stream_ptr()), "cl3d_pwmlp_fwd_out")
     return out
 
 
-def pwmlp_bwd(grad_out, out, ab_pm, wp, query_xyz, support_xyz, idx, ymax, ymin, arg, stats, gamma, radius):
+def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, ysel, aq, sq, karg, stats, gamma,
+              radius):
     """-> (grad_ab_pm (B,N,2Cop), grad_wp (3,Cout), dgamma (Cout), dbeta (Cout))"""
     B, N, C2 = ab_pm.shape
     Cout, M, K = out.shape[1], out.shape[2], idx.shape[2]
@@ -237,7 +257,8 @@ def pwmlp_bwd(grad_out, out, ab_pm, wp, query_xyz, support_xyz, idx, ymax, ymin,
     dgb = torch.empty(2, Cout, dtype=F32, device=dev)
     grad_ab = torch.empty(B, N, C2, dtype=F32, device=dev)
     grad_wp = torch.empty(3, Cout, dtype=F32, device=dev)
-    check(L.cl3d_pwmlp_bwd(ptr(grad_out), ptr(out), ptr(ab_pm), ptr(wp), ptr(query_xyz), ptr(support_xyz), ptr(idx),
-                           ptr(ymax), ptr(ymin), ptr(arg), ptr(stats), ptr(gamma), B, N, M, K, Cout, float(radius),
-                           ptr(partial), ptr(dgb), ptr(grad_ab), ptr(grad_wp), stream_ptr()), "cl3d_pwmlp_bwd")
+    check(L.cl3d_pwmlp_bwd(ptr(grad_out), ptr(out), ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(idx),
+                           ptr(csr_off), ptr(csr_ent), ptr(ysel), ptr(aq), ptr(sq), ptr(karg), ptr(stats), ptr(gamma),
+                           B, N, M, K, Cout, float(radius), ptr(partial), ptr(dgb), ptr(grad_ab), ptr(grad_wp),
+                           stream_ptr()), "cl3d_pwmlp_bwd")
     return grad_ab, grad_wp, dgb[0], dgb[1]

@@ -36,6 +36,7 @@ class NeighborList:
     def __init__(self, idx, ncount, idx_mask, N):
         self.idx, self.ncount, self._idx_mask, self.N = idx, ncount, idx_mask, N
         self._csr = None
+        self._csr_all = None
 
     @property
     def idx_mask(self):
@@ -44,9 +45,17 @@ class NeighborList:
         return self._idx_mask
 
     def csr(self):
+        """transposed lists over the COUNTED slots (k < ncount): avg/sum families"""
         if self._csr is None:
             self._csr = ops.build_csr(self.idx, self.ncount, self.N)
         return self._csr
+
+    def csr_all_slots(self):
+        """transposed lists over ALL K slots (BatchNorm2d of PointWiseMLP sees every slot)"""
+        if self._csr_all is None:
+            full = torch.full_like(self.ncount, self.idx.shape[2])
+            self._csr_all = ops.build_csr(self.idx, full, self.N)
+        return self._csr_all
 
 
 _CACHE = collections.OrderedDict()

@@ -56,6 +56,9 @@ typedef void* cl3d_stream_t; /* cudaStream_t */
 int cl3d_version(void);
 const char* cl3d_last_error(void);
 int cl3d_padded_channels(int C);
+/* Every point-major buffer the gather kernels read (feat_pm, g_pm, ab_pm, aq) must be followed by
+ * CL3D_PM_SLACK readable floats: lanes past a row's channel chunk load without a predicate and discard. */
+#define CL3D_PM_SLACK 256
 /* number of SMs of the current device (grid sizing); negative on error */
 int cl3d_sm_count(void);
 /* kernels launched by this library in this process so far (for bench.py's gpu_launches) */
@@ -196,24 +199,31 @@ int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, l
                long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk, void* workspace,
                size_t workspace_bytes, cl3d_stream_t stream);
 
-/* ab_pm (B,N,2*Cop): row = [A | Bv], Cop = cl3d_padded_channels(Cout);  wp (Cout,3) = conv weight columns 0..2.
- * fwd_stats: ymax,ymin (B,Cout,M); arg (B,M,Cop) uint16 = argmax | argmin<<8 (K <= 255);
- *            bn_partial (cl3d_agg_num_tiles(B,M), 2, Cout) -> cl3d_bn_finalize with count = B*M*K.
- * fwd_out  : out (B,Cout,M) = relu(sc*(sc>=0 ? ymax : ymin) + sh).
- * bwd      : partial = scratch (cl3d_agg_num_tiles(B,M), 3, Cout); dgamma_dbeta (2,Cout);
- *            grad_ab_pm (B,N,2*Cop) (zero-filled by the call, then accumulated with fp32 red.add);
- *            grad_wp (3,Cout). */
-int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* query_xyz,
-                         const float* support_xyz, const int* idx, int B, int N, int M, int K, int Cout,
-                         float radius, float* ymax, float* ymin, unsigned short* arg, float* bn_partial,
-                         cl3d_stream_t stream);
-int cl3d_pwmlp_fwd_out(const float* ymax, const float* ymin, const float* save_stats, const float* gamma,
-                       const float* beta, int B, int M, int Cout, float* out, cl3d_stream_t stream);
+/* Fused PointWiseMLP (pwmlp.cu).  Cop = cl3d_padded_channels(Cout), Cpa = cl3d_padded_channels(C+3).
+ *   cl3d_to_point_major_aug : (B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | xyz/r | 0]
+ *   ab_pm (B,N,2*Cop)       : row = [A | T],  A = (Wc-Wr) f,  T = sgn*(Wr f + Wp s/r)   (one cl3d_sgemm)
+ *   wp (Cout,3), sgn (Cout) : conv weight columns 0..2; sign(gamma) as +-1.0
+ * fwd_stats : ysel (B,Cout,M) selected extremum of y; aq, sq (B,M,Cop) a' and sum_k bv; karg (B,M,Cop) uint8
+ *             first arg-max slot (K <= 255); bn_partial (cl3d_agg_num_tiles(B,M), 2, Cout) -> cl3d_bn_finalize
+ *             with count = B*M*K.
+ * fwd_out   : out (B,Cout,M) = relu(sc*ysel + sh).
+ * bwd       : csr_off/csr_ent = cl3d_build_csr over ALL K slots (ncount = K); partial = scratch
+ *             (cl3d_agg_num_tiles(B,M), 3, Cout); dgamma_dbeta (2,Cout); grad_ab_pm (B,N,2*Cop) fully written
+ *             (dense part stored, sparse part added with fp32 red.add); grad_wp (3,Cout) = the -sum da' (x) q/r
+ *             part of d/dWp (the rest comes out of the weight-gradient product). */
+int cl3d_to_point_major_aug(const float* in_cn, const float* xyz, int B, int C, int N, float radius,
+                            float* out_nc, cl3d_stream_t stream);
+int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* sgn, const float* query_xyz,
+                         const int* idx, int B, int N, int M, int K, int Cout, float radius, float* ysel,
+                         float* aq, float* sq, unsigned char* karg, float* bn_partial, cl3d_stream_t stream);
+int cl3d_pwmlp_fwd_out(const float* ysel, const float* save_stats, const float* gamma, const float* beta,
+                       int B, int M, int Cout, float* out, cl3d_stream_t stream);
 int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, const float* wp,
-                   const float* query_xyz, const float* support_xyz, const int* idx, const float* ymax,
-                   const float* ymin, const unsigned short* arg, const float* save_stats,
-                   const float* gamma, int B, int N, int M, int K, int Cout, float radius, float* partial,
-                   float* dgamma_dbeta, float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream);
+                   const float* sgn, const float* query_xyz, const int* idx, const int* csr_off,
+                   const int* csr_ent, const float* ysel, const float* aq, const float* sq,
+                   const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
+                   int M, int K, int Cout, float radius, float* partial, float* dgamma_dbeta,
+                   float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream);
 
 #ifdef __cplusplus
 }
