@@ -33,6 +33,8 @@ SIGNATURES = {
     "cl3d_group_points_grad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "cl3d_grid_subsample_workspace_bytes": (_sz, [_i, _i, _i]),
     "cl3d_grid_subsample": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "cl3d_gather_max_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cl3d_gather_max_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "cl3d_to_point_major": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "cl3d_to_channel_major": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "cl3d_agg_num_tiles": (_i, [_i, _i]),

@@ -262,3 +262,46 @@ def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, y
                            B, N, M, K, Cout, float(radius), ptr(partial), ptr(dgb), ptr(grad_ab), ptr(grad_wp),
                            stream_ptr()), "cl3d_pwmlp_bwd")
     return grad_ab, grad_wp, dgb[0], dgb[1]
+
+
+# --------------------------------------------------------------------------------------------------
+# grid subsampling, fused max-pool
+# --------------------------------------------------------------------------------------------------
+def grid_subsample(points, mask, npoint, sampleDl):
+    """-> (sub_xyz (B,m,3) f32, sub_mask (B,m) i32); bit-exact with masked_grid_subsampling_gpu.cu:11-153"""
+    require_cuda(points, "points", F32)
+    require_cuda(mask, "mask", I32)
+    B, n, _ = points.shape
+    m = int(npoint)
+    L = _lib.lib()
+    dev = points.device
+    sub = torch.empty(B, m, 3, dtype=F32, device=dev)
+    sm = torch.empty(B, m, dtype=I32, device=dev)
+    wsb = L.cl3d_grid_subsample_workspace_bytes(B, n, m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(L.cl3d_grid_subsample(ptr(points), ptr(mask), B, n, m, float(sampleDl), ptr(sub), ptr(sm), ptr(ws), wsb,
+                                stream_ptr()), "cl3d_grid_subsample")
+    return sub, sm
+
+
+def gather_max(features, idx):
+    """out[b,c,q] = max_k features[b,c,idx[b,q,k]] -> (out (B,C,M), arg (B,M,Cp) uint8)"""
+    require_cuda(features, "features", F32)
+    require_cuda(idx, "idx", I32)
+    B, C, N = features.shape
+    M, K = idx.shape[1], idx.shape[2]
+    feat_pm = to_point_major(features)
+    out = torch.empty(B, C, M, dtype=F32, device=features.device)
+    arg = torch.empty(B, M, feat_pm.shape[2], dtype=torch.uint8, device=features.device)
+    check(_lib.lib().cl3d_gather_max_fwd(ptr(feat_pm), ptr(idx), B, N, M, K, C, ptr(out), ptr(arg), stream_ptr()),
+          "cl3d_gather_max_fwd")
+    return out, arg
+
+
+def gather_max_grad(grad_out, idx, arg, N):
+    B, C, M = grad_out.shape
+    K = idx.shape[2]
+    g_pm = torch.empty(B, N, padded_channels(C), dtype=F32, device=grad_out.device)
+    check(_lib.lib().cl3d_gather_max_bwd(ptr(grad_out), ptr(idx), ptr(arg), B, N, M, K, C, ptr(g_pm), stream_ptr()),
+          "cl3d_gather_max_bwd")
+    return to_channel_major(g_pm, C)

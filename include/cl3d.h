@@ -120,6 +120,14 @@ int cl3d_grid_subsample(const float* points, const int* mask, int B, int n, int 
                         float* sub_xyz, int* sub_mask, void* workspace, size_t workspace_bytes,
                         cl3d_stream_t stream);
 
+/* Fused neighbourhood max-pool (body of MaskedMaxPool, pt_utils.py:195-201) and its gradient.
+ *   feat_pm (B,N,Cp) point-major (+CL3D_PM_SLACK); out (B,C,M); arg (B,M,Cp) uint8 first arg-max slot (K <= 255)
+ *   bwd: grad_pm (B,N,Cp) point-major, zero-filled by the call then accumulated (one red.add row per query). */
+int cl3d_gather_max_fwd(const float* feat_pm, const int* idx, int B, int N, int M, int K, int C, float* out,
+                        unsigned char* arg, cl3d_stream_t stream);
+int cl3d_gather_max_bwd(const float* grad_out, const int* idx, const unsigned char* arg, int B, int N, int M,
+                        int K, int C, float* grad_pm, cl3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Layout: channel-major (B,C,N) <-> point-major (B,N,Cp), Cp = cl3d_padded_channels(C), pad = 0.
  * ---------------------------------------------------------------------------------------------- */
