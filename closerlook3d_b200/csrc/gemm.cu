@@ -17,7 +17,7 @@ namespace cl3d {
 
 constexpr int kBM = 128, kBK = 16;
 
-template <int TN>
+template <int TN, bool VEC>
 __global__ void __launch_bounds__(256) sgemm_tiled_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
                                                           const float* __restrict__ B, long long sb_k,
                                                           long long sb_n, int M, int N, int K, int k_per_split,
@@ -35,36 +35,103 @@ __global__ void __launch_bounds__(256) sgemm_tiled_kernel(const float* __restric
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  float ra[8], rb[TN];
+  // VEC: every operand is read as float4 along its unit-stride dimension (host guarantees 16-byte alignment,
+  // strides and extents that are multiples of 4, so a vector is entirely inside or entirely outside)
+  constexpr int NVB = (BN * kBK / 4 + 255) / 256;  // float4 of the B tile per thread
+  float ra[8], rb[VEC ? NVB * 4 : TN];
 
   auto load_tiles = [&](int k0) {
+    if constexpr (VEC) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int e = threadIdx.x + 256 * r;
-      const int mm = a_k_fast ? e / kBK : e % kBM, kk = a_k_fast ? e % kBK : e / kBM;
-      const int m = m0 + mm, k = k0 + kk;
-      ra[r] = (m < M && k < kend) ? __ldg(A + m * sa_m + k * sa_k) : 0.f;
-    }
+      for (int r = 0; r < 2; ++r) {
+        const int e = threadIdx.x + 256 * r;  // 512 float4 of the A tile
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a_k_fast) {
+          const int mm = e >> 2, kk = (e & 3) * 4;
+          const int m = m0 + mm, k = k0 + kk;
+          if (m < M && k < kend) v = __ldg(reinterpret_cast<const float4*>(A + m * sa_m + k));
+        } else {
+          const int kk = e >> 5, mm = (e & 31) * 4;
+          const int m = m0 + mm, k = k0 + kk;
+          if (m < M && k < kend) v = __ldg(reinterpret_cast<const float4*>(A + k * sa_k + m));
+        }
+        ra[r * 4 + 0] = v.x; ra[r * 4 + 1] = v.y; ra[r * 4 + 2] = v.z; ra[r * 4 + 3] = v.w;
+      }
 #pragma unroll
-    for (int r = 0; r < TN; ++r) {
-      const int e = threadIdx.x + 256 * r;
-      const int nn = b_k_fast ? e / kBK : e % BN, kk = b_k_fast ? e % kBK : e / BN;
-      const int n = n0 + nn, k = k0 + kk;
-      rb[r] = (n < N && k < kend) ? __ldg(B + k * sb_k + n * sb_n) : 0.f;
+      for (int r = 0; r < NVB; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < BN * kBK / 4) {
+          if (b_k_fast) {
+            const int nn = e >> 2, kk = (e & 3) * 4;
+            const int n = n0 + nn, k = k0 + kk;
+            if (n < N && k < kend) v = __ldg(reinterpret_cast<const float4*>(B + n * sb_n + k));
+          } else {
+            const int kk = e / (BN / 4), nn = (e % (BN / 4)) * 4;
+            const int n = n0 + nn, k = k0 + kk;
+            if (n < N && k < kend) v = __ldg(reinterpret_cast<const float4*>(B + k * sb_k + n));
+          }
+        }
+        rb[r * 4 + 0] = v.x; rb[r * 4 + 1] = v.y; rb[r * 4 + 2] = v.z; rb[r * 4 + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        const int mm = a_k_fast ? e / kBK : e % kBM, kk = a_k_fast ? e % kBK : e / kBM;
+        const int m = m0 + mm, k = k0 + kk;
+        ra[r] = (m < M && k < kend) ? __ldg(A + m * sa_m + k * sa_k) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < TN; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        const int nn = b_k_fast ? e / kBK : e % BN, kk = b_k_fast ? e % kBK : e / BN;
+        const int n = n0 + nn, k = k0 + kk;
+        rb[r] = (n < N && k < kend) ? __ldg(B + k * sb_k + n * sb_n) : 0.f;
+      }
     }
   };
   auto store_tiles = [&]() {
+    if constexpr (VEC) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int e = threadIdx.x + 256 * r;
-      const int mm = a_k_fast ? e / kBK : e % kBM, kk = a_k_fast ? e % kBK : e / kBM;
-      sA[kk][mm] = ra[r];
-    }
+      for (int r = 0; r < 2; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        if (a_k_fast) {
+          const int mm = e >> 2, kk = (e & 3) * 4;
 #pragma unroll
-    for (int r = 0; r < TN; ++r) {
-      const int e = threadIdx.x + 256 * r;
-      const int nn = b_k_fast ? e / kBK : e % BN, kk = b_k_fast ? e % kBK : e / BN;
-      sB[kk][nn] = rb[r];
+          for (int t = 0; t < 4; ++t) sA[kk + t][mm] = ra[r * 4 + t];
+        } else {
+          const int kk = e >> 5, mm = (e & 31) * 4;
+          *reinterpret_cast<float4*>(&sA[kk][mm]) = make_float4(ra[r * 4], ra[r * 4 + 1], ra[r * 4 + 2], ra[r * 4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NVB; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        if (e < BN * kBK / 4) {
+          if (b_k_fast) {
+            const int nn = e >> 2, kk = (e & 3) * 4;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) sB[kk + t][nn] = rb[r * 4 + t];
+          } else {
+            const int kk = e / (BN / 4), nn = (e % (BN / 4)) * 4;
+            *reinterpret_cast<float4*>(&sB[kk][nn]) = make_float4(rb[r * 4], rb[r * 4 + 1], rb[r * 4 + 2], rb[r * 4 + 3]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        const int mm = a_k_fast ? e / kBK : e % kBM, kk = a_k_fast ? e % kBK : e / kBM;
+        sA[kk][mm] = ra[r];
+      }
+#pragma unroll
+      for (int r = 0; r < TN; ++r) {
+        const int e = threadIdx.x + 256 * r;
+        const int nn = b_k_fast ? e / kBK : e % BN, kk = b_k_fast ? e % kBK : e / BN;
+        sB[kk][nn] = rb[r];
+      }
     }
   };
 
@@ -125,7 +192,16 @@ template <int TN>
 static void launch_sgemm(dim3 grid, cudaStream_t stream, const float* a, long long sa_m, long long sa_k, const float* b,
                          long long sb_k, long long sb_n, int M, int N, int K, int kps, float* c, long long ldc,
                          float* partial) {
-  sgemm_tiled_kernel<TN><<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial);
+  // float4 path: unit stride along one dimension of each operand, everything else a multiple of 4 floats
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool va = al16(a) && ((sa_k == 1 && sa_m % 4 == 0 && K % 4 == 0 && kps % 4 == 0) ||
+                              (sa_m == 1 && sa_k % 4 == 0 && M % 4 == 0));
+  const bool vb = al16(b) && ((sb_k == 1 && sb_n % 4 == 0 && K % 4 == 0 && kps % 4 == 0) ||
+                              (sb_n == 1 && sb_k % 4 == 0 && N % 4 == 0));
+  if (va && vb && (sa_k == 1 || sa_m == 1) && (sb_k == 1 || sb_n == 1))
+    sgemm_tiled_kernel<TN, true><<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial);
+  else
+    sgemm_tiled_kernel<TN, false><<<grid, 256, 0, stream>>>(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial);
   CL3D_LAUNCHED(1);
 }
 

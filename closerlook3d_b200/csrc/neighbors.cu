@@ -207,17 +207,74 @@ __device__ __forceinline__ u64 make_key(float d2, int idx) {
   return ((u64)__float_as_uint(d2) << 32) | (unsigned)idx;  // d2 >= +0 -> bit pattern is monotone
 }
 
+// Warp bitonic sort of up to 32*E 64-bit keys (element i = e*32 + lane), ascending; missing elements = ~0.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[E]) {
+  const int lane = lane_id();
+  constexpr int n = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {  // partner lives in another register of the same lane
+        const int de = j >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & de) == 0) {
+            const bool up = (((e * 32 + lane) & k) == 0);
+            const u64 a = key[e], b = key[e | de];
+            const bool sw = (a > b) == up;
+            key[e] = sw ? b : a;
+            key[e | de] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const u64 other = __shfl_xor_sync(0xffffffffu, key[e], j);
+          const bool up = (((e * 32 + lane) & k) == 0);
+          const bool lower = ((lane & j) == 0);
+          const u64 mn = other < key[e] ? other : key[e], mx = other < key[e] ? key[e] : other;
+          key[e] = (lower == up) ? mn : mx;
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void emit_sorted(const u64* L, int cnt, int* s_sorted, int K) {
+  const int lane = lane_id();
+  u64 key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) key[e] = (e * 32 + lane) < cnt ? L[e * 32 + lane] : ~0ull;
+  warp_bitonic_sort<E>(key);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < cnt && i < K) s_sorted[i] = (int)(unsigned)(key[e] & 0xffffffffu);
+  }
+}
+
 // L[0..cnt) holds the reference's candidate list (any order; unique indices).  Emits the first K of the list
 // sorted by (d2, index) -- identical to the reference's stable sort of an index-ascending list
 // (masked_ordered_ball_query_gpu.cu:77) -- then the cyclic padding (:83-86) and masks (:79-93).
 __device__ __forceinline__ void emit_query(const u64* L, int cnt, int* s_sorted, int K, int qm, int* __restrict__ idx_out,
                                            int* __restrict__ mask_out, int* __restrict__ ncount_out) {
   const int lane = lane_id();
-  for (int i = lane; i < cnt; i += 32) {
-    const u64 my = L[i];
-    int rho = 0;
-    for (int j = 0; j < cnt; ++j) rho += (L[j] < my) ? 1 : 0;
-    if (rho < K) s_sorted[rho] = (int)(unsigned)(my & 0xffffffffu);
+  if (cnt <= 32) {
+    emit_sorted<1>(L, cnt, s_sorted, K);
+  } else if (cnt <= 64) {
+    emit_sorted<2>(L, cnt, s_sorted, K);
+  } else if (cnt <= 128) {
+    emit_sorted<4>(L, cnt, s_sorted, K);
+  } else {  // rank by counting (O(cnt^2/32)); only reached for nsample > 42
+    for (int i = lane; i < cnt; i += 32) {
+      const u64 my = L[i];
+      int rho = 0;
+      for (int j = 0; j < cnt; ++j) rho += (L[j] < my) ? 1 : 0;
+      if (rho < K) s_sorted[rho] = (int)(unsigned)(my & 0xffffffffu);
+    }
   }
   __syncwarp();
   for (int k = lane; k < K; k += 32) {
@@ -273,7 +330,8 @@ __device__ __forceinline__ int brute_force_collect(LoadXYZ load, int n_valid, fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// brute-force kernel for small clouds: the cloud's xyz lives in shared memory
+// brute-force kernel for small clouds: the cloud lives in shared memory as float4, padded to a multiple of 32
+// with far-away sentinels (and sentinels behind the valid prefix), so the scan loop has no bounds checks
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
     const float* __restrict__ query_xyz, const float* __restrict__ support_xyz, const int* __restrict__ query_mask,
@@ -282,9 +340,10 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.y;
   const int cap3k = 3 * K;
-  float* s_xyz = reinterpret_cast<float*>(smem_raw);                            // N*3 floats
-  u64* s_list = reinterpret_cast<u64*>(smem_raw + align_up((size_t)N * 12, 16));  // warps * 3K keys
-  int* s_sorted = reinterpret_cast<int*>(s_list + (size_t)kBQWarps * cap3k);      // warps * K
+  const int npad = (N + 31) & ~31;
+  float4* s_pts = reinterpret_cast<float4*>(smem_raw);                               // npad points
+  u64* s_list = reinterpret_cast<u64*>(smem_raw + (size_t)npad * 16);                // warps * 3K keys
+  int* s_sorted = reinterpret_cast<int*>(s_list + (size_t)kBQWarps * cap3k);         // warps * K
   __shared__ int s_first;
   if (threadIdx.x == 0) s_first = N;
   __syncthreads();
@@ -294,10 +353,14 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
   for (int i = threadIdx.x; i < N; i += blockDim.x)
     if (sm[i] == 0) { first = i; break; }
   if (first < N) atomicMin(&s_first, first);
-  for (int i = threadIdx.x; i < N * 3; i += blockDim.x) s_xyz[i] = sx[i];
   __syncthreads();
   const int n_valid = s_first;
-  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x)
+    s_pts[i] = i < n_valid ? make_float4(sx[i * 3 + 0], sx[i * 3 + 1], sx[i * 3 + 2], 0.f)
+                           : make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);  // never inside any ball
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const float r2 = __fmul_rn(radius, radius);
   u64* L = s_list + (size_t)warp * cap3k;
   int* srt = s_sorted + (size_t)warp * K;
@@ -306,13 +369,39 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
   for (int q = q0 + warp; q < q1; q += kBQWarps) {
     const float* qp = query_xyz + ((size_t)b * M + q) * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
-    int cnt = brute_force_collect(
-        [&](int i, float& x, float& y, float& z) {
-          x = s_xyz[i * 3 + 0];
-          y = s_xyz[i * 3 + 1];
-          z = s_xyz[i * 3 + 2];
-        },
-        n_valid, qx, qy, qz, r2, cap3k, L);
+    // index-order scan (:48-70): the first 3K in-radius points, in index order
+    int T = 0;
+    for (int base = 0; base < npad; base += 32) {
+      const float4 p = s_pts[base + lane];
+      const float d2 = ref_d2(qx, qy, qz, p.x, p.y, p.z);
+      const bool in = d2 < r2;
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const int pos = T + __popc(m & lt);
+        if (pos < cap3k) L[pos] = make_key(d2, base + lane);
+      }
+      T += __popc(m);
+    }
+    __syncwarp();
+    int cnt = T;
+    if (T >= cap3k) {
+      // rare: more than 3K in the ball -> the global nearest may lie beyond the cut (:59-62,72-75)
+      u64 best = ~0ull;
+      for (int base = 0; base < npad; base += 32) {
+        const float4 p = s_pts[base + lane];
+        const float d2 = ref_d2(qx, qy, qz, p.x, p.y, p.z);
+        if (d2 < r2) {
+          const u64 key = make_key(d2, base + lane);
+          best = key < best ? key : best;
+        }
+      }
+      best = warp_min_u64(best);
+      const u64 last = L[cap3k - 1];
+      __syncwarp();
+      if (lane == 0 && (unsigned)(best & 0xffffffffu) > (unsigned)(last & 0xffffffffu)) L[cap3k - 1] = best;
+      __syncwarp();
+      cnt = cap3k;
+    }
     const size_t o = ((size_t)b * M + q);
     emit_query(L, cnt, srt, K, query_mask[o], idx + o * K, idx_mask ? idx_mask + o * K : nullptr,
                ncount ? ncount + o : nullptr);
@@ -591,7 +680,7 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
   CL3D_REQUIRE(algo != CL3D_BQ_BRUTE || N <= 8192, "cl3d_ball_query: brute-force path limited to N <= 8192");
   const bool brute = algo == CL3D_BQ_BRUTE || (algo == CL3D_BQ_AUTO && N <= kBruteMaxN);
   if (brute) {
-    size_t smem = align_up((size_t)N * 12, 16) + (size_t)kBQWarps * cap3k * 8 + (size_t)kBQWarps * K * 4;
+    size_t smem = (size_t)((N + 31) & ~31) * 16 + (size_t)kBQWarps * cap3k * 8 + (size_t)kBQWarps * K * 4;
     const int qpc = 64;  // queries per CTA (8 per warp): amortises the cloud load, keeps >= 148 CTAs at c2
     static bool attr_set = false;
     if (!attr_set) {

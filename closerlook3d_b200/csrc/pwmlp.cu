@@ -419,6 +419,44 @@ __global__ void __launch_bounds__(256) to_point_major_aug_kernel(const float* __
   }
 }
 
+// W (Cout, 3+2C) = [Wp | Wc | Wr], gamma -> wcat (2*Cop, C+3), wp (Cout,3), sgn (Cout)   (see file header)
+__global__ void pwmlp_prep_kernel(const float* __restrict__ W, const float* __restrict__ gamma, int C, int Cout, int Cop,
+                                  int Cpa, float* __restrict__ wcat, float* __restrict__ wp, float* __restrict__ sgn) {
+  const int row = blockIdx.x;  // 0 .. 2*Cop-1
+  const bool trow = row >= Cop;
+  const int o = trow ? row - Cop : row;
+  const int W3 = 3 + 2 * C;
+  for (int c = threadIdx.x; c < Cpa; c += blockDim.x) {  // rows padded to Cpa (zeros): float4-friendly
+    float v = 0.f;
+    if (o < Cout && c < C + 3) {
+      const float sg = gamma[o] >= 0.f ? 1.f : -1.f;
+      if (!trow) v = c < C ? W[(size_t)o * W3 + 3 + c] - W[(size_t)o * W3 + 3 + C + c] : 0.f;
+      else v = sg * (c < C ? W[(size_t)o * W3 + 3 + C + c] : W[(size_t)o * W3 + (c - C)]);
+      if (!trow && c < 3) wp[o * 3 + c] = W[(size_t)o * W3 + c];
+      if (!trow && c == 0) sgn[o] = sg;
+    }
+    wcat[(size_t)row * Cpa + c] = v;
+  }
+}
+
+// gwcat (2*Cop, C+3), grad_wp (3,Cout), sgn -> gW (Cout, 3+2C) = [dWp | dWc | dWr]
+__global__ void pwmlp_wgrad_kernel(const float* __restrict__ gwcat, const float* __restrict__ grad_wp,
+                                   const float* __restrict__ sgn, int C, int Cout, int Cop, int Cpa,
+                                   float* __restrict__ gW) {
+  const int o = blockIdx.x;
+  const int W3 = 3 + 2 * C;
+  const float sg = sgn[o];
+  const float* gA = gwcat + (size_t)o * Cpa;
+  const float* gT = gwcat + (size_t)(Cop + o) * Cpa;
+  for (int c = threadIdx.x; c < W3; c += blockDim.x) {
+    float v;
+    if (c < 3) v = sg * gT[C + c] + grad_wp[(size_t)c * Cout + o];  // Wp: T rows' xyz columns + the a' part
+    else if (c < 3 + C) v = gA[c - 3];                               // Wc
+    else v = sg * gT[c - 3 - C] - gA[c - 3 - C];                     // Wr
+    gW[(size_t)o * W3 + c] = v;
+  }
+}
+
 static int pw_ci(int Cop) {
   int ci = ceil_div(Cop, 32);
   return ci > kPWMaxCI ? kPWMaxCI : ci;
@@ -463,6 +501,25 @@ extern "C" int cl3d_to_point_major_aug(const float* in_cn, const float* xyz, int
   to_point_major_aug_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(in_cn, xyz, C, N, Cpa, 1.0f / radius, out_nc);
   CL3D_LAUNCHED(1);
   return check_launch("to_point_major_aug_kernel");
+}
+
+extern "C" int cl3d_pwmlp_prep_weights(const float* conv_weight, const float* gamma, int C, int Cout, float* wcat,
+                                       float* wp, float* sgn, cl3d_stream_t stream_) {
+  CL3D_REQUIRE(conv_weight && gamma && wcat && wp && sgn && C >= 1 && Cout >= 1, "cl3d_pwmlp_prep_weights: bad arguments");
+  const int Cop = padded_channels(Cout);
+  pwmlp_prep_kernel<<<2 * Cop, 128, 0, (cudaStream_t)stream_>>>(conv_weight, gamma, C, Cout, Cop,
+                                                                padded_channels(C + 3), wcat, wp, sgn);
+  CL3D_LAUNCHED(1);
+  return check_launch("pwmlp_prep_kernel");
+}
+
+extern "C" int cl3d_pwmlp_weight_grad(const float* gwcat, const float* grad_wp, const float* sgn, int C, int Cout,
+                                      float* grad_conv_weight, cl3d_stream_t stream_) {
+  CL3D_REQUIRE(gwcat && grad_wp && sgn && grad_conv_weight && C >= 1 && Cout >= 1, "cl3d_pwmlp_weight_grad: bad arguments");
+  pwmlp_wgrad_kernel<<<Cout, 128, 0, (cudaStream_t)stream_>>>(gwcat, grad_wp, sgn, C, Cout, padded_channels(Cout),
+                                                              padded_channels(C + 3), grad_conv_weight);
+  CL3D_LAUNCHED(1);
+  return check_launch("pwmlp_wgrad_kernel");
 }
 
 extern "C" int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* sgn, const float* query_xyz,

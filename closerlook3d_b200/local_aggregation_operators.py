@@ -38,7 +38,8 @@ class _FusedAggBNReLU(Function):
     def forward(ctx, features, p0, p1, bn_weight, bn_bias, spec, nl, query_xyz, support_xyz, bn):
         B, C, N = features.shape
         M = query_xyz.shape[1]
-        feat_pm = ops.to_point_major(features)
+        feat_pm = ops.to_point_major(features)   # overlaps the neighbour search running on the side stream
+        nl.wait()
         training = bn.training or (bn.running_mean is None)
         agg, partial = ops.agg_fwd(spec.family, spec.reduction, feat_pm, query_xyz, support_xyz, nl.idx, nl.ncount,
                                    p0, p1, C, spec.radius, spec.normalize, spec.shared, spec.nkp, spec.extent,
@@ -50,6 +51,8 @@ class _FusedAggBNReLU(Function):
                 momentum = 1.0 / float(bn.num_batches_tracked)
         stats = ops.bn_finalize(partial, C, B * M, bn.eps, momentum, training, bn.running_mean, bn.running_var)
         out = ops.bn_relu_fwd(agg, stats, bn_weight, bn_bias)
+        if any(ctx.needs_input_grad):
+            nl.prefetch_csr(all_slots=False)      # transposed lists for the backward, built behind the forward
         ctx.spec, ctx.nl, ctx.training, ctx.N = spec, nl, training, N
         needs_feat = spec.family in (ops.FAM_ADAPTIVE_DP, ops.FAM_PSEUDOGRID)
         ctx.save_for_backward(agg, stats, bn_weight, bn_bias, query_xyz, support_xyz, p0, p1,

@@ -221,6 +221,25 @@ def to_point_major_aug(x_cn, xyz, radius):
     return out
 
 
+def pwmlp_prep_weights(conv_weight, gamma, C, Cout):
+    """-> wcat (2Cop, Cpa) rows zero-padded to Cpa = padded(C+3), wp (Cout,3), sgn (Cout)"""
+    dev = conv_weight.device
+    Cop = padded_channels(Cout)
+    wcat = torch.empty(2 * Cop, padded_channels(C + 3), dtype=F32, device=dev)
+    wp = torch.empty(Cout, 3, dtype=F32, device=dev)
+    sgn = torch.empty(Cout, dtype=F32, device=dev)
+    check(_lib.lib().cl3d_pwmlp_prep_weights(ptr(conv_weight), ptr(gamma), C, Cout, ptr(wcat), ptr(wp), ptr(sgn),
+                                             stream_ptr()), "cl3d_pwmlp_prep_weights")
+    return wcat, wp, sgn
+
+
+def pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout):
+    gW = torch.empty(Cout, 3 + 2 * C, 1, 1, dtype=F32, device=gwcat.device)
+    check(_lib.lib().cl3d_pwmlp_weight_grad(ptr(gwcat), ptr(grad_wp), ptr(sgn), C, Cout, ptr(gW), stream_ptr()),
+          "cl3d_pwmlp_weight_grad")
+    return gW
+
+
 def pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, idx, Cout, radius):
     B, N, _ = ab_pm.shape
     M, K = idx.shape[1], idx.shape[2]

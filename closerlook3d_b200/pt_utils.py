@@ -31,31 +31,85 @@ from . import ops
 # neighbour lists + cache
 # --------------------------------------------------------------------------------------------------
 class NeighborList:
-    """idx (B,M,K) i32, ncount (B,M) i32 [+ idx_mask (B,M,K) i32 on demand, CSR lists on demand]."""
+    """idx (B,M,K) i32, ncount (B,M) i32 [+ idx_mask (B,M,K) i32 on demand, CSR lists on demand].
+
+    The search (and, when a backward will follow, the transposed lists) is enqueued on a side stream so that it
+    overlaps the layout change / per-point product of the caller; `wait()` / `csr()` make the current stream
+    wait for it.  Every use of the side stream starts with side.wait_stream(current), so memory allocated there
+    is never recycled under a pending consumer."""
 
     def __init__(self, idx, ncount, idx_mask, N):
         self.idx, self.ncount, self._idx_mask, self.N = idx, ncount, idx_mask, N
         self._csr = None
         self._csr_all = None
+        self.event = None
+        self._csr_event = None
+        self._csr_all_event = None
+
+    def wait(self):
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+        return self
 
     @property
     def idx_mask(self):
-        if self._idx_mask is None:  # derive: mask[k] = k < ncount  (valid queries) ; 0 for padded queries
+        if self._idx_mask is None:
             raise RuntimeError("idx_mask was not requested for this neighbour list")
         return self._idx_mask
+
+    def _build(self, all_slots):
+        if all_slots:
+            full = torch.full_like(self.ncount, self.idx.shape[2])
+            return ops.build_csr(self.idx, full, self.N)
+        return ops.build_csr(self.idx, self.ncount, self.N)
+
+    def prefetch_csr(self, all_slots=False):
+        """enqueue the transposed-list build on the side stream right behind the search"""
+        if (self._csr_all if all_slots else self._csr) is not None:
+            return
+        side = _side_stream(self.idx.device)
+        if self.event is not None:
+            side.wait_event(self.event)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            csr = self._build(all_slots)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        if all_slots:
+            self._csr_all, self._csr_all_event = csr, ev
+        else:
+            self._csr, self._csr_event = csr, ev
 
     def csr(self):
         """transposed lists over the COUNTED slots (k < ncount): avg/sum families"""
         if self._csr is None:
-            self._csr = ops.build_csr(self.idx, self.ncount, self.N)
+            self.wait()
+            self._csr = self._build(False)
+        elif self._csr_event is not None:
+            torch.cuda.current_stream().wait_event(self._csr_event)
         return self._csr
 
     def csr_all_slots(self):
         """transposed lists over ALL K slots (BatchNorm2d of PointWiseMLP sees every slot)"""
         if self._csr_all is None:
-            full = torch.full_like(self.ncount, self.idx.shape[2])
-            self._csr_all = ops.build_csr(self.idx, full, self.N)
+            self.wait()
+            self._csr_all = self._build(True)
+        elif self._csr_all_event is not None:
+            torch.cuda.current_stream().wait_event(self._csr_all_event)
         return self._csr_all
+
+
+_SIDE = {}
+overlap_enabled = True  # run the neighbour search on a side stream (fork/join), see NeighborList
+
+
+def _side_stream(device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _SIDE.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE[key] = st
+    return st
 
 
 _CACHE = collections.OrderedDict()
@@ -72,9 +126,11 @@ def clear_neighbor_cache():
     _CACHE.clear()
 
 
-def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, need_mask=False):
+def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, need_mask=False, overlap=None):
     """Ball-query neighbour list for (query, support, radius, nsample), cached on tensor identity
-    (data pointer + version; the cache keeps the key tensors alive so pointers cannot be recycled)."""
+    (data pointer + version; the cache keeps the key tensors alive so pointers cannot be recycled).
+    With overlap (default: pt_utils.overlap_enabled) the search runs on a side stream; consumers call
+    nl.wait() (the fused operators do) before touching nl.idx / nl.ncount."""
     key = (_key(query_xyz), _key(support_xyz), _key(query_mask), _key(support_mask), float(radius), int(nsample))
     if cache_enabled:
         hit = _CACHE.get(key)
@@ -83,9 +139,22 @@ def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
             cache_stats["hit"] += 1
             return hit[0]
     cache_stats["miss"] += 1
-    idx, idx_mask, ncount = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
-                                           want_mask=need_mask, want_ncount=True)
-    nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
+    overlap = overlap_enabled if overlap is None else overlap
+    if overlap:
+        cur = torch.cuda.current_stream()
+        side = _side_stream(query_xyz.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            idx, idx_mask, ncount = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
+                                                   want_mask=need_mask, want_ncount=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
+        nl.event = ev
+    else:
+        idx, idx_mask, ncount = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
+                                               want_mask=need_mask, want_ncount=True)
+        nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
     if cache_enabled:
         _CACHE[key] = (nl, (query_xyz, support_xyz, query_mask, support_mask))
         while len(_CACHE) > _CACHE_SIZE:
@@ -118,7 +187,7 @@ class MaskedOrderedBallQuery(Function):
 
     @staticmethod
     def forward(ctx, radius, nsample, query_xyz, support_xyz, query_mask, support_mask):
-        nl = neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, need_mask=True)
+        nl = neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, need_mask=True).wait()
         ctx.mark_non_differentiable(nl.idx, nl.idx_mask)
         return nl.idx, nl.idx_mask
 
@@ -248,7 +317,7 @@ class MaskedMaxPool(nn.Module):
         sub_xyz, sub_mask = masked_grid_subsampling(xyz, mask, self.npoint, self.sampleDl)
         sub_xyz = sub_xyz.contiguous()
         sub_mask = sub_mask.contiguous()
-        nl = neighbors(sub_xyz, xyz, sub_mask, mask, self.radius, self.nsample)
+        nl = neighbors(sub_xyz, xyz, sub_mask, mask, self.radius, self.nsample).wait()
         sub_features = _GatherMax.apply(features.contiguous(), nl.idx)
         return sub_xyz, sub_mask, sub_features
 
@@ -265,6 +334,6 @@ class MaskedUpsample(nn.Module):
             idx, _ = masked_nearest_query(up_xyz, xyz, up_mask, mask)  # (B,M,1)
             return grouping_operation(features, idx)[..., 0].contiguous()
         elif self.mode == 'max':
-            nl = neighbors(up_xyz, xyz, up_mask, mask, self.radius, self.nsample)
+            nl = neighbors(up_xyz, xyz, up_mask, mask, self.radius, self.nsample).wait()
             return _GatherMax.apply(features.contiguous(), nl.idx)
         raise NotImplementedError(f"mode:{self.mode} not supported in MaskedUpsample")

@@ -5,9 +5,8 @@ The conv weight W (Cout, 3+2C) = [Wp | Wc | Wr] and sgn = sign(BN gamma) are fol
     wcat (2*Cop, C+3):  rows 0..Cout-1       = [Wc - Wr | 0 0 0]        -> A  = (Wc-Wr) f
                         rows Cop..Cop+Cout-1 = sgn * [Wr | Wp]          -> T  = sgn (Wr f + Wp s/r)
 so that ONE per-point product over the augmented point-major matrix [f | s/r] yields both terms
-(csrc/pwmlp.cu explains why y[o,q,k] = a'[q][o] + sgn*T[j_k][o] is the reference's function).  Only this
-folding / unfolding of the small weight matrices is done with torch ops; all per-point and per-neighbour work
-is in libcl3d.
+(csrc/pwmlp.cu explains why y[o,q,k] = a'[q][o] + sgn*T[j_k][o] is the reference's function).  The folding / unfolding of the small weight matrices is one tiny kernel each way (cl3d_pwmlp_prep_weights /
+cl3d_pwmlp_weight_grad).
 """
 import torch
 from torch.autograd import Function
@@ -22,17 +21,14 @@ class _FusedPointWiseMLP(Function):
         M, K = nl.idx.shape[1], nl.idx.shape[2]
         Cout = conv_weight.shape[0]
         Cop = ops.padded_channels(Cout)
-        W = conv_weight.view(Cout, 3 + 2 * C)
-        wp = W[:, :3].contiguous()
-        sgn = torch.where(bn_weight >= 0, 1.0, -1.0).to(torch.float32).contiguous()
-        wcat = torch.zeros(2 * Cop, C + 3, dtype=torch.float32, device=features.device)
-        wcat[:Cout, :C] = W[:, 3:3 + C] - W[:, 3 + C:]
-        wcat[Cop:Cop + Cout, :C] = sgn[:, None] * W[:, 3 + C:]
-        wcat[Cop:Cop + Cout, C:] = sgn[:, None] * wp
+        wcat, wp, sgn = ops.pwmlp_prep_weights(conv_weight.contiguous(), bn_weight, C, Cout)
         fa_pm = ops.to_point_major_aug(features, support_xyz, radius)          # (B,N,Cpa)
         Cpa = fa_pm.shape[2]
-        # AB[p][n] = sum_c fa[p][c] * wcat[n][c]
-        ab_pm = ops.sgemm(fa_pm, Cpa, 1, wcat, 1, C + 3, B * N, 2 * Cop, C + 3).view(B, N, 2 * Cop)
+        # AB[p][n] = sum_c fa[p][c] * wcat[n][c]   (both row-padded to Cpa with zeros -> k runs over Cpa)
+        ab_pm = ops.sgemm(fa_pm, Cpa, 1, wcat, 1, Cpa, B * N, 2 * Cop, Cpa).view(B, N, 2 * Cop)
+        nl.wait()                                   # the search ran on the side stream, overlapping the product
+        if any(ctx.needs_input_grad):
+            nl.prefetch_csr(all_slots=True)         # lists for the backward, built behind the forward kernels
         ysel, aq, sq, karg, partial = ops.pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, nl.idx, Cout, radius)
         training = bn.training or (bn.running_mean is None)
         momentum = bn.momentum if bn.momentum is not None else 0.0
@@ -59,15 +55,13 @@ class _FusedPointWiseMLP(Function):
                                                         off, ent, ysel, aq, sq, karg, stats, bn_weight, ctx.radius)
         P = B * N
         Cp = ops.padded_channels(C)
-        # d/dfeat (point-major) = grad_AB (P x 2Cop) @ wcat[:, :C] (2Cop x C)
-        gf_pm = ops.sgemm(grad_ab, 2 * Cop, 1, wcat, C + 3, 1, P, C, 2 * Cop, ldc=Cp).view(B, N, Cp)
+        # d/dfeat (point-major) = grad_AB (P x 2Cop) @ wcat[:, :Cp] (2Cop x Cp; columns >= C are unused)
+        gf_pm = ops.sgemm(grad_ab, 2 * Cop, 1, wcat, Cpa, 1, P, Cp, 2 * Cop, ldc=Cp).view(B, N, Cp)
         grad_feat = ops.to_channel_major(gf_pm, C)
         # d/dwcat (2Cop x (C+3)) = grad_AB^T (2Cop x P) @ fa (P x (C+3)): long reduction -> split-K
         splitk = max(1, min(256, P // 256))
-        gwcat = ops.sgemm(grad_ab, 1, 2 * Cop, fa_pm, Cpa, 1, 2 * Cop, C + 3, P, splitk=splitk)
-        gA = gwcat[:Cout, :C]
-        gT = sgn[:, None] * gwcat[Cop:Cop + Cout]
-        gW = torch.cat([gT[:, C:] + grad_wp.t(), gA, gT[:, :C] - gA], dim=1).view(Cout, 3 + 2 * C, 1, 1)
+        gwcat = ops.sgemm(grad_ab, 1, 2 * Cop, fa_pm, Cpa, 1, 2 * Cop, Cpa, P, splitk=splitk)
+        gW = ops.pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout)
         return grad_feat, gW, dgamma, dbeta, None, None, None, None, None
 
 

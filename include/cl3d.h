@@ -219,6 +219,12 @@ int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, l
  *             (cl3d_agg_num_tiles(B,M), 3, Cout); dgamma_dbeta (2,Cout); grad_ab_pm (B,N,2*Cop) fully written
  *             (dense part stored, sparse part added with fp32 red.add); grad_wp (3,Cout) = the -sum da' (x) q/r
  *             part of d/dWp (the rest comes out of the weight-gradient product). */
+/* conv weight (Cout, 3+2C) = [Wp|Wc|Wr] + BN gamma -> wcat (2*Cop, Cpa) (rows zero-padded to Cpa), wp (Cout,3),
+ * sgn (Cout); and back: d/dwcat (2*Cop, Cpa) + grad_wp (3,Cout) -> d/d(conv weight) (Cout, 3+2C). */
+int cl3d_pwmlp_prep_weights(const float* conv_weight, const float* gamma, int C, int Cout, float* wcat,
+                            float* wp, float* sgn, cl3d_stream_t stream);
+int cl3d_pwmlp_weight_grad(const float* gwcat, const float* grad_wp, const float* sgn, int C, int Cout,
+                           float* grad_conv_weight, cl3d_stream_t stream);
 int cl3d_to_point_major_aug(const float* in_cn, const float* xyz, int B, int C, int N, float radius,
                             float* out_nc, cl3d_stream_t stream);
 int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* sgn, const float* query_xyz,
