@@ -47,7 +47,7 @@ struct AggArgs {
   float* partial;            // fwd: bn partial (ntiles,2,C); bwd: param-grad partial (gridDim.x, P)
   int B, N, M, K, C, Cp;
   int reduction, normalize, shared, nkp, influence;
-  float inv_radius, extent;
+  float inv_radius, extent, inv_extent;
   int ntiles;
 };
 
@@ -110,11 +110,12 @@ __device__ __forceinline__ float family_weight(const LaneParams<FAM, CI>& lp, in
 
 // PseudoGrid influence of kernel point kp on relative position dp (:385-403), mask applied by caller
 __device__ __forceinline__ float pg_influence(float dx, float dy, float dz, const float* kp, int influence,
-                                              float extent) {
+                                              float inv_extent) {
   if (influence == 1) return 1.f;  // 'constant'
   const float ex = dx - kp[0], ey = dy - kp[1], ez = dz - kp[2];
   const float sq = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-  const float h = 1.f - __fdiv_rn(sqrtf(sq), extent);  // clamp(1 - sqrt(sq)/extent, min=0)  :397
+  // clamp(1 - sqrt(sq)/extent, min=0) :397 ; torch's CUDA `tensor / python_scalar` multiplies by the fp32 reciprocal
+  const float h = 1.f - __fmul_rn(sqrtf(sq), inv_extent);
   return h > 0.f ? h : 0.f;
 }
 
@@ -124,7 +125,7 @@ constexpr int rows_in_flight() {  // independent row loads per lane before they 
 }
 template <int FAM, bool BWD>
 constexpr int num_acc() {
-  return FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : ((BWD && FAM == CL3D_FAM_ADAPTIVE_DP) ? 4 : 1);
+  return (FAM == CL3D_FAM_PSEUDOGRID && BWD) ? kMaxKP : ((BWD && FAM == CL3D_FAM_ADAPTIVE_DP) ? 4 : 1);
 }
 
 // shared-memory carve-up (per CTA): per-warp slot arrays (dp + row index, influences / scales) + output tile
@@ -147,12 +148,33 @@ __host__ __device__ inline SmemLayout smem_layout(int chunkC, int red_floats) {
   return L;
 }
 
-// one staged slot: applies the family to the row values v[CI] of that slot
-template <int FAM, int CI, bool BWD, int NACC>
+// one staged slot: applies the family to the row values v[CI] of that slot.
+// PseudoGrid forward uses  out[c] += f[c] * (sum_k' Wk[k',c] h[k'])  (one accumulator per channel, Wk in
+// registers); PseudoGrid backward accumulates T[k'][c] = sum_e g[c] h[k',e] (needed for d/dWk anyway).
+template <int FAM, int CI, bool BWD, int NACC, int NWK>
 __device__ __forceinline__ void apply_slot(const float (&v)[CI], const float4& dp, const float* __restrict__ hk,
-                                           const LaneParams<FAM, CI>& lp, float (&acc)[NACC][CI]) {
-  if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
+                                           const LaneParams<FAM, CI>& lp, const float (&wk)[NWK][CI],
+                                           float (&acc)[NACC][CI]) {
+  if constexpr (FAM == CL3D_FAM_PSEUDOGRID && !BWD) {
     const float4* h4 = reinterpret_cast<const float4*>(hk);  // 16 influences of this slot (0 beyond nkp)
+    float w[CI];
+#pragma unroll
+    for (int i = 0; i < CI; ++i) w[i] = 0.f;
+#pragma unroll
+    for (int k4 = 0; k4 < kMaxKP / 4; ++k4) {
+      const float4 h = h4[k4];
+#pragma unroll
+      for (int i = 0; i < CI; ++i) {
+        w[i] = fmaf(h.x, wk[k4 * 4 + 0][i], w[i]);
+        w[i] = fmaf(h.y, wk[k4 * 4 + 1][i], w[i]);
+        w[i] = fmaf(h.z, wk[k4 * 4 + 2][i], w[i]);
+        w[i] = fmaf(h.w, wk[k4 * 4 + 3][i], w[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CI; ++i) acc[0][i] = fmaf(v[i], w[i], acc[0][i]);
+  } else if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
+    const float4* h4 = reinterpret_cast<const float4*>(hk);
 #pragma unroll
     for (int k4 = 0; k4 < kMaxKP / 4; ++k4) {
       const float4 h = h4[k4];
@@ -189,33 +211,57 @@ __device__ __forceinline__ void apply_slot(const float (&v)[CI], const float4& d
 // immediate offsets (+32 floats each).  Lanes past the chunk read whatever follows (the next row, or the
 // CL3D_PM_SLACK floats every point-major buffer carries after its last row); their results are never stored.
 // Rows are loaded U at a time straight into registers (U*CI independent loads in flight per lane).
-template <int FAM, int CI, bool BWD, int NACC>
+template <int FAM, int CI, bool BWD, int NACC, int NWK>
 __device__ __forceinline__ void consume_slots(const float* __restrict__ lbase,
                                               const float4* __restrict__ s_dp, const float* __restrict__ s_h, int n,
-                                              const LaneParams<FAM, CI>& lp, float (&acc)[NACC][CI]) {
+                                              const LaneParams<FAM, CI>& lp, const float (&wk)[NWK][CI],
+                                              float (&acc)[NACC][CI]) {
   constexpr int U = rows_in_flight<FAM>();
   constexpr int HS = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;  // floats of s_h per slot
-  int s = 0;
-  for (; s + U <= n; s += U) {
-    float4 dp[U];
-    float v[U][CI];
+  // software pipeline: group g+1 is loaded into the other register set while group g is consumed
+  auto load_group = [&](int s0, float4 (&dp)[U], float (&v)[U][CI]) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      dp[u] = s_dp[s + u];
+      dp[u] = s_dp[s0 + u];
       const float* row = lbase + __float_as_uint(dp[u].w);
 #pragma unroll
       for (int i = 0; i < CI; ++i) v[u][i] = __ldg(row + 32 * i);  // lanes past the chunk read slack (unused)
     }
+  };
+  auto apply_group = [&](int s0, const float4 (&dp)[U], const float (&v)[U][CI]) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) apply_slot<FAM, CI, BWD, NACC>(v[u], dp[u], s_h + (size_t)(s + u) * HS, lp, acc);
+    for (int u = 0; u < U; ++u) apply_slot<FAM, CI, BWD, NACC, NWK>(v[u], dp[u], s_h + (size_t)(s0 + u) * HS, lp, wk, acc);
+  };
+  const int ng = n / U;
+  if constexpr (FAM == CL3D_FAM_PSEUDOGRID && BWD) {
+    // accumulator-heavy kernel (few resident warps): hide the row latency inside the warp
+    float4 dpA[U], dpB[U];
+    float vA[U][CI], vB[U][CI];
+    if (ng > 0) load_group(0, dpA, vA);
+    int g = 0;
+    for (; g + 2 <= ng; g += 2) {
+      load_group((g + 1) * U, dpB, vB);
+      apply_group(g * U, dpA, vA);
+      if (g + 2 < ng) load_group((g + 2) * U, dpA, vA);
+      apply_group((g + 1) * U, dpB, vB);
+    }
+    if (g < ng) apply_group(g * U, dpA, vA);
+  } else {
+    // light families: few registers, many resident warps hide the latency
+    for (int g = 0; g < ng; ++g) {
+      float4 dp[U];
+      float v[U][CI];
+      load_group(g * U, dp, v);
+      apply_group(g * U, dp, v);
+    }
   }
-  for (; s < n; ++s) {
+  for (int s = ng * U; s < n; ++s) {
     const float4 dp = s_dp[s];
     const float* row = lbase + __float_as_uint(dp.w);
     float v[CI];
 #pragma unroll
     for (int i = 0; i < CI; ++i) v[i] = __ldg(row + 32 * i);
-    apply_slot<FAM, CI, BWD, NACC>(v, dp, s_h + (size_t)s * HS, lp, acc);
+    apply_slot<FAM, CI, BWD, NACC, NWK>(v, dp, s_h + (size_t)s * HS, lp, wk, acc);
   }
 }
 
@@ -223,7 +269,7 @@ __device__ __forceinline__ void consume_slots(const float* __restrict__ lbase,
 // forward
 // =================================================================================================
 template <int FAM, int CI>
-__global__ void __launch_bounds__(kAggWarps * 32) agg_fwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2 : 1) agg_fwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * 32 * CI;
@@ -281,22 +327,17 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_fwd_kernel(const AggArgs a
           s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)j * (unsigned)a.Cp));
           if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
             for (int kp = 0; kp < a.nkp; ++kp)
-              s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
+              s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.inv_extent);
             for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[lane * kMaxKP + kp] = 0.f;
           }
         }
         __syncwarp();
-        consume_slots<FAM, CI, false, NACC>(feat, s_dp, s_h, rows, lp, acc);
+        consume_slots<FAM, CI, false, NACC, NWK>(feat, s_dp, s_h, rows, lp, wk, acc);
         __syncwarp();  // slots are rewritten by the next round / query
       }
       if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
 #pragma unroll
-        for (int i = 0; i < CI; ++i) {
-          float r = 0.f;
-#pragma unroll
-          for (int kp = 0; kp < kMaxKP; ++kp) r = fmaf(acc[kp][i], wk[kp][i], r);  // sum_k' Wk[k',c] t[k',c]  :418-419
-          res[i] = r;
-        }
+        for (int i = 0; i < CI; ++i) res[i] = acc[0][i];  // sum_m f[c,m] * sum_k' Wk[k',c] h[k',m]   (:415-419)
       } else {
 #pragma unroll
         for (int i = 0; i < CI; ++i)
@@ -335,41 +376,50 @@ __host__ __device__ constexpr int params_per_channel(int nkp) {
   return FAM == CL3D_FAM_ADAPTIVE_DP ? 4 : (FAM == CL3D_FAM_PSEUDOGRID ? nkp : 0);
 }
 
+// PseudoGrid backward keeps its kernel weights and parameter-gradient accumulators in shared memory (they are
+// touched once per support point, not per neighbour), which halves the register count (2 CTAs per SM).
+__host__ __device__ inline size_t pg_bwd_extra_floats(int CI) {
+  return (size_t)kMaxKP * 32 * CI /*wk*/ + (size_t)kAggWarps * kMaxKP * 32 * CI /*per-warp pacc*/;
+}
+
 template <int FAM, int CI>
-__global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2 : 1) agg_bwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * 32 * CI;
   const int chunkC = min(32 * CI, a.Cp - c0);
   constexpr int NACC = num_acc<FAM, true>();
-  constexpr bool HASP = FAM == CL3D_FAM_ADAPTIVE_DP || FAM == CL3D_FAM_PSEUDOGRID;
-  constexpr int HS = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;
+  constexpr bool PG = FAM == CL3D_FAM_PSEUDOGRID;
+  constexpr bool AW = FAM == CL3D_FAM_ADAPTIVE_DP;
+  constexpr bool HASP = AW || PG;
+  constexpr int HS = PG ? kMaxKP : 1;
   const int ppc = params_per_channel<FAM>(a.nkp);
   const SmemLayout L = smem_layout(32 * CI, ppc * 32 * CI);
   float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
   float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * kSlots * kMaxKP;
   float* s_out = reinterpret_cast<float*>(smem + L.out_off);
   float* s_red = reinterpret_cast<float*>(smem + L.red_off);
+  float* s_wk = reinterpret_cast<float*>(smem + L.total);                 // [kMaxKP][32*CI]      (PG only)
+  float* s_pacc = s_wk + (size_t)kMaxKP * 32 * CI + (size_t)warp * kMaxKP * 32 * CI;  // per warp (PG only)
 
   LaneParams<FAM, CI> lp;
   load_lane_params<FAM, CI>(lp, a, c0, lane);
   bool ok[CI];
 #pragma unroll
   for (int i = 0; i < CI; ++i) ok[i] = lane + 32 * i < chunkC;
-  constexpr int NWK = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;
-  float wk[NWK][CI];
-#pragma unroll
-  for (int kp = 0; kp < NWK; ++kp)
-#pragma unroll
-    for (int i = 0; i < CI; ++i) {
-      const int c = c0 + lane + 32 * i;
-      wk[kp][i] = (FAM == CL3D_FAM_PSEUDOGRID && kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
+  const float wk_dummy[1][CI] = {};
+  if constexpr (PG) {
+    for (int e = threadIdx.x; e < kMaxKP * 32 * CI; e += blockDim.x) {
+      const int kp = e / (32 * CI), c = c0 + e % (32 * CI);
+      s_wk[e] = (kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
     }
-  // per-lane parameter-gradient accumulators over all points this warp handles
-  constexpr int NP = HASP ? NACC : 1;
-  float pacc[NP][CI];
+    for (int e = lane; e < kMaxKP * 32 * CI; e += 32) s_pacc[e] = 0.f;
+    __syncthreads();
+  }
+  // AdaptiveWeight: per-lane parameter-gradient accumulators (x,y,z,bias) over all points this warp handles
+  float pacc[AW ? 4 : 1][CI];
 #pragma unroll
-  for (int s = 0; s < NP; ++s)
+  for (int s = 0; s < (AW ? 4 : 1); ++s)
 #pragma unroll
     for (int i = 0; i < CI; ++i) pacc[s][i] = 0.f;
 
@@ -410,16 +460,16 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
               dz = __fmul_rn(dz, a.inv_radius);
             }
             s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)q * (unsigned)a.Cp));
-            if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
+            if constexpr (PG) {
               for (int kp = 0; kp < a.nkp; ++kp)
-                s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.extent);
+                s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.inv_extent);
               for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[lane * kMaxKP + kp] = 0.f;
             } else {
               s_h[lane * HS] = a.reduction == CL3D_REDUCE_AVG ? __fdiv_rn(1.f, (float)ncnt[q]) : 1.f;
             }
           }
           __syncwarp();
-          consume_slots<FAM, CI, true, NACC>(gpm, s_dp, s_h, rows, lp, acc);
+          consume_slots<FAM, CI, true, NACC, 1>(gpm, s_dp, s_h, rows, lp, wk_dummy, acc);
           __syncwarp();
         }
         // ---- epilogue: gradient w.r.t. this support point's features, parameter gradients
@@ -428,7 +478,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
 #pragma unroll
           for (int i = 0; i < CI; ++i) {
             const float f = ok[i] ? __ldg(frow + 32 * i) : 0.f;
-            if constexpr (FAM == CL3D_FAM_ADAPTIVE_DP) {
+            if constexpr (AW) {
               res[i] = fmaf(lp.c[i], acc[2][i], fmaf(lp.b[i], acc[1][i], fmaf(lp.a[i], acc[0][i], lp.d[i] * acc[3][i])));
 #pragma unroll
               for (int s = 0; s < 4; ++s) pacc[s][i] = fmaf(f, acc[s][i], pacc[s][i]);
@@ -436,8 +486,9 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
               float r = 0.f;
 #pragma unroll
               for (int kp = 0; kp < kMaxKP; ++kp) {
-                r = fmaf(wk[kp][i], acc[kp][i], r);
-                pacc[kp][i] = fmaf(f, acc[kp][i], pacc[kp][i]);
+                const int o = kp * 32 * CI + lane + 32 * i;
+                r = fmaf(s_wk[o], acc[kp][i], r);
+                s_pacc[o] = fmaf(f, acc[kp][i], s_pacc[o]);  // this warp's private accumulator row
               }
               res[i] = r;
             }
@@ -459,29 +510,298 @@ __global__ void __launch_bounds__(kAggWarps * 32) agg_bwd_kernel(const AggArgs a
     }
     __syncthreads();
   }
-  // ---- CTA-level reduction of the parameter-gradient accumulators (warps take turns: fixed order)
-  if constexpr (HASP) {
+  // ---- CTA-level reduction of the parameter-gradient accumulators, fixed order over the warps
+  if constexpr (AW) {
     for (int w = 0; w < kAggWarps; ++w) {
       if (warp == w) {
 #pragma unroll
-        for (int s = 0; s < NP; ++s) {
-          if (s < ppc) {
+        for (int s = 0; s < 4; ++s)
 #pragma unroll
-            for (int i = 0; i < CI; ++i) {
-              float* p = s_red + (size_t)s * 32 * CI + lane + 32 * i;
-              *p = (w == 0) ? pacc[s][i] : (*p + pacc[s][i]);
-            }
+          for (int i = 0; i < CI; ++i) {
+            float* p = s_red + (size_t)s * 32 * CI + lane + 32 * i;
+            *p = (w == 0) ? pacc[s][i] : (*p + pacc[s][i]);
           }
-        }
       }
       __syncthreads();
     }
+  }
+  if constexpr (PG) {
+    __syncthreads();
+    const float* all = s_wk + (size_t)kMaxKP * 32 * CI;  // [warps][kMaxKP][32*CI]
+    for (int e = threadIdx.x; e < ppc * 32 * CI; e += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAggWarps; ++w) t += all[(size_t)w * kMaxKP * 32 * CI + e];
+      s_red[e] = t;
+    }
+    __syncthreads();
+  }
+  if constexpr (HASP) {
     // partial layout: (gridDim.x, ppc, C)
     for (int e = threadIdx.x; e < ppc * 32 * CI; e += blockDim.x) {
       const int s = e / (32 * CI), cl = e % (32 * CI);
       const int c = c0 + cl;
       if (c < a.C) a.partial[((size_t)blockIdx.x * ppc + s) * a.C + c] = s_red[e];
     }
+  }
+}
+
+// =================================================================================================
+// PosPool sin_cos: pair ownership.  Channel c = axis*2F + t (t<F: sin, t>=F: cos of the SAME argument
+// 100*dp_axis/dim_t, local_aggregation_operators.py:70-83), so a lane owns the PAIR (axis,t) = both channels
+// and evaluates one division + one sincosf per (neighbour, pair) instead of a sinf AND a cosf per channel.
+// Pair p = axis*F + t ; chunk of 32*PI pairs per CTA (blockIdx.y).
+// =================================================================================================
+template <int PI>
+struct PairLane {
+  unsigned osin[PI], ocos[PI];  // channel offsets inside a row
+  float dim[PI], rdim[PI];
+  int axis[PI];
+};
+
+template <int PI>
+__device__ __forceinline__ void load_pair_lane(PairLane<PI>& pl, const AggArgs& a, int p0, int lane) {
+  const int F = a.C / 6, npairs = 3 * F;
+#pragma unroll
+  for (int i = 0; i < PI; ++i) {
+    int p = p0 + lane + 32 * i;
+    if (p >= npairs) p = npairs - 1;  // duplicate work of a valid pair; its result is not written
+    const int ax = p / F, t = p % F;
+    pl.axis[i] = ax;
+    pl.osin[i] = (unsigned)(ax * 2 * F + t);
+    pl.ocos[i] = pl.osin[i] + (unsigned)F;
+    pl.dim[i] = a.p0[t];
+    pl.rdim[i] = __frcp_rn(pl.dim[i]);
+  }
+}
+
+// sin and cos of x for |x| < ~1e4 (here |x| <= 100*|dp| ~ 1e2): Cody-Waite reduction by pi/2 in three steps,
+// then the classic single-precision minimax polynomials on [-pi/4, pi/4]; ~1 ulp, branch-free, no slow path
+// (the library sincosf inlines a Payne-Hanek path whose code size thrashed the instruction cache here).
+__device__ __forceinline__ void sincos_small(float x, float& sn, float& cs) {
+  const float j = rintf(x * 0.636619747f);
+  float r = __fmaf_rn(j, -1.57079601e+00f, x);
+  r = __fmaf_rn(j, -3.13916473e-07f, r);
+  r = __fmaf_rn(j, -5.39030253e-15f, r);
+  const int q = (int)j;
+  const float r2 = r * r;
+  float ps = __fmaf_rn(r2, -1.95152959e-4f, 8.33216087e-3f);
+  ps = __fmaf_rn(ps, r2, -1.66666546e-1f);
+  ps = __fmaf_rn(ps * r2, r, r);                      // sin(r)
+  float pc = __fmaf_rn(r2, 2.44331571e-5f, -1.38873163e-3f);
+  pc = __fmaf_rn(pc, r2, 4.16666457e-2f);
+  pc = __fmaf_rn(pc, r2, -0.5f);
+  pc = __fmaf_rn(pc, r2, 1.0f);                       // cos(r)
+  const bool swap = q & 1;
+  float s0 = swap ? pc : ps, c0 = swap ? ps : pc;
+  sn = (q & 2) ? -s0 : s0;
+  cs = ((q + 1) & 2) ? -c0 : c0;
+}
+
+// n / d with a precomputed reciprocal: one Newton correction on the quotient (correctly rounded except in rare
+// double-rounding cases; d >= 1 here, no overflow / denormals)
+__device__ __forceinline__ float div_by(float n, float d, float rcp_d) {
+  const float q0 = n * rcp_d;
+  const float r = __fmaf_rn(-d, q0, n);
+  return __fmaf_rn(r, rcp_d, q0);
+}
+
+template <int PI, bool BWD>
+__device__ __forceinline__ void consume_pairs(const float* __restrict__ base, const float4* __restrict__ s_dp,
+                                              const float* __restrict__ s_h, int n, const PairLane<PI>& pl,
+                                              float (&as)[PI], float (&ac)[PI]) {
+  constexpr int U = 2;
+  int s = 0;
+  for (; s + U <= n; s += U) {
+    float4 dp[U];
+    float vs[U][PI], vc[U][PI];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dp[u] = s_dp[s + u];
+      const float* row = base + __float_as_uint(dp[u].w);
+#pragma unroll
+      for (int i = 0; i < PI; ++i) {
+        vs[u][i] = __ldg(row + pl.osin[i]);
+        vc[u][i] = __ldg(row + pl.ocos[i]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float sc = BWD ? s_h[s + u] : 1.f;
+#pragma unroll
+      for (int i = 0; i < PI; ++i) {
+        const float pcomp = pl.axis[i] == 0 ? dp[u].x : (pl.axis[i] == 1 ? dp[u].y : dp[u].z);
+        const float arg = div_by(__fmul_rn(100.f, pcomp), pl.dim[i], pl.rdim[i]);  // torch.div(alpha*dp, dim_mat)
+        float sn, cs;
+        sincos_small(arg, sn, cs);
+        as[i] = fmaf(BWD ? vs[u][i] * sc : vs[u][i], sn, as[i]);
+        ac[i] = fmaf(BWD ? vc[u][i] * sc : vc[u][i], cs, ac[i]);
+      }
+    }
+  }
+  for (; s < n; ++s) {
+    const float4 dp = s_dp[s];
+    const float* row = base + __float_as_uint(dp.w);
+    const float sc = BWD ? s_h[s] : 1.f;
+#pragma unroll
+    for (int i = 0; i < PI; ++i) {
+      const float vs = __ldg(row + pl.osin[i]), vc = __ldg(row + pl.ocos[i]);
+      const float pcomp = pl.axis[i] == 0 ? dp.x : (pl.axis[i] == 1 ? dp.y : dp.z);
+      const float arg = div_by(__fmul_rn(100.f, pcomp), pl.dim[i], pl.rdim[i]);
+      float sn, cs;
+      sincos_small(arg, sn, cs);
+      as[i] = fmaf(BWD ? vs * sc : vs, sn, as[i]);
+      ac[i] = fmaf(BWD ? vc * sc : vc, cs, ac[i]);
+    }
+  }
+}
+
+// tile row r in [0, 2*32*PI): half h = r / (32*PI) (0 sin, 1 cos), pair p0 + r % (32*PI) -> channel or -1
+__device__ __forceinline__ int pair_row_channel(int r, int p0, int pairs_per_cta, int F) {
+  const int h = r / pairs_per_cta, p = p0 + r % pairs_per_cta;
+  if (p >= 3 * F) return -1;
+  return (p / F) * 2 * F + (p % F) + h * F;
+}
+
+template <int PI>
+__global__ void __launch_bounds__(kAggWarps * 32) sincos_fwd_kernel(const AggArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.y * 32 * PI;
+  const int F = a.C / 6;
+  const SmemLayout L = smem_layout(2 * 32 * PI, 0);
+  float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
+  float* s_out = reinterpret_cast<float*>(smem + L.out_off);
+  const int tiles_per_cloud = (a.M + kTile - 1) / kTile;
+  const int b = blockIdx.x / tiles_per_cloud;
+  const int q0 = (blockIdx.x % tiles_per_cloud) * kTile;
+  PairLane<PI> pl;
+  load_pair_lane<PI>(pl, a, p0, lane);
+  const float* feat = a.feat_pm + (size_t)b * a.N * a.Cp;
+  const float* sxyz = a.support_xyz + (size_t)b * a.N * 3;
+  for (int ql = warp; ql < kTile; ql += kAggWarps) {
+    const int q = q0 + ql;
+    float rs[PI], rc[PI];
+#pragma unroll
+    for (int i = 0; i < PI; ++i) rs[i] = rc[i] = 0.f;
+    if (q < a.M) {
+      const size_t gq = (size_t)b * a.M + q;
+      const int nrows = a.ncount[gq];
+      const float qx = a.query_xyz[gq * 3 + 0], qy = a.query_xyz[gq * 3 + 1], qz = a.query_xyz[gq * 3 + 2];
+      for (int k0 = 0; k0 < nrows; k0 += kSlots) {
+        const int rows = min(kSlots, nrows - k0);
+        if (lane < rows) {
+          const int j = a.idx[gq * a.K + k0 + lane];
+          float dx = __fsub_rn(sxyz[j * 3 + 0], qx), dy = __fsub_rn(sxyz[j * 3 + 1], qy),
+                dz = __fsub_rn(sxyz[j * 3 + 2], qz);
+          if (a.normalize) {
+            dx = __fmul_rn(dx, a.inv_radius);
+            dy = __fmul_rn(dy, a.inv_radius);
+            dz = __fmul_rn(dz, a.inv_radius);
+          }
+          s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)j * (unsigned)a.Cp));
+        }
+        __syncwarp();
+        consume_pairs<PI, false>(feat, s_dp, nullptr, rows, pl, rs, rc);
+        __syncwarp();
+      }
+      if (a.reduction == CL3D_REDUCE_AVG) {
+#pragma unroll
+        for (int i = 0; i < PI; ++i) {
+          rs[i] = __fdiv_rn(rs[i], (float)nrows);
+          rc[i] = __fdiv_rn(rc[i], (float)nrows);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PI; ++i) {
+      s_out[(size_t)(lane + 32 * i) * (kTile + 1) + ql] = rs[i];
+      s_out[(size_t)(32 * PI + lane + 32 * i) * (kTile + 1) + ql] = rc[i];
+    }
+  }
+  __syncthreads();
+  const int q = q0 + lane;
+  for (int r = warp; r < 2 * 32 * PI; r += kAggWarps) {
+    const int c = pair_row_channel(r, p0, 32 * PI, F);
+    if (c < 0) continue;
+    float v = 0.f;
+    if (q < a.M) {
+      v = s_out[(size_t)r * (kTile + 1) + lane];
+      a.out[((size_t)b * a.C + c) * a.M + q] = v;
+    }
+    if (a.partial) {
+      const float s1 = warp_sum(v), s2 = warp_sum(v * v);
+      if (lane == 0) {
+        a.partial[((size_t)blockIdx.x * 2 + 0) * a.C + c] = s1;
+        a.partial[((size_t)blockIdx.x * 2 + 1) * a.C + c] = s2;
+      }
+    }
+  }
+}
+
+template <int PI>
+__global__ void __launch_bounds__(kAggWarps * 32) sincos_bwd_kernel(const AggArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.y * 32 * PI;
+  const int F = a.C / 6;
+  const SmemLayout L = smem_layout(2 * 32 * PI, 0);
+  float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
+  float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * kSlots * kMaxKP;
+  float* s_out = reinterpret_cast<float*>(smem + L.out_off);
+  PairLane<PI> pl;
+  load_pair_lane<PI>(pl, a, p0, lane);
+  const int tiles_per_cloud = (a.N + kTile - 1) / kTile;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_cloud;
+    const int j0 = (tile % tiles_per_cloud) * kTile;
+    const float* gpm = a.g_pm + (size_t)b * a.M * a.Cp;
+    const float* qxyz = a.query_xyz + (size_t)b * a.M * 3;
+    const int* ncnt = a.ncount + (size_t)b * a.M;
+    const int* off = a.csr_off + (size_t)b * (a.N + 1);
+    const int* ent = a.csr_ent + (size_t)b * a.M * a.K;
+    for (int jl = warp; jl < kTile; jl += kAggWarps) {
+      const int j = j0 + jl;
+      float rs[PI], rc[PI];
+#pragma unroll
+      for (int i = 0; i < PI; ++i) rs[i] = rc[i] = 0.f;
+      if (j < a.N) {
+        const int e0 = off[j], e1 = off[j + 1];
+        const float* sp = a.support_xyz + ((size_t)b * a.N + j) * 3;
+        const float px = sp[0], py = sp[1], pz = sp[2];
+        for (int eb = e0; eb < e1; eb += kSlots) {
+          const int rows = min(kSlots, e1 - eb);
+          if (lane < rows) {
+            const int q = ent[eb + lane] / a.K;
+            float dx = __fsub_rn(px, qxyz[q * 3 + 0]), dy = __fsub_rn(py, qxyz[q * 3 + 1]),
+                  dz = __fsub_rn(pz, qxyz[q * 3 + 2]);
+            if (a.normalize) {
+              dx = __fmul_rn(dx, a.inv_radius);
+              dy = __fmul_rn(dy, a.inv_radius);
+              dz = __fmul_rn(dz, a.inv_radius);
+            }
+            s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)q * (unsigned)a.Cp));
+            s_h[lane] = a.reduction == CL3D_REDUCE_AVG ? __fdiv_rn(1.f, (float)ncnt[q]) : 1.f;
+          }
+          __syncwarp();
+          consume_pairs<PI, true>(gpm, s_dp, s_h, rows, pl, rs, rc);
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PI; ++i) {
+        s_out[(size_t)(lane + 32 * i) * (kTile + 1) + jl] = rs[i];
+        s_out[(size_t)(32 * PI + lane + 32 * i) * (kTile + 1) + jl] = rc[i];
+      }
+    }
+    __syncthreads();
+    const int j = j0 + lane;
+    for (int r = warp; r < 2 * 32 * PI; r += kAggWarps) {
+      const int c = pair_row_channel(r, p0, 32 * PI, F);
+      if (c < 0) continue;
+      if (j < a.N) a.out[((size_t)b * a.C + c) * a.N + j] = s_out[(size_t)r * (kTile + 1) + lane];
+    }
+    __syncthreads();
   }
 }
 
@@ -505,10 +825,11 @@ static int launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   const int nchunks = ceil_div(a.Cp, 32 * CI);
   const int ppc = params_per_channel<FAM>(a.nkp);
   const SmemLayout L = smem_layout(32 * CI, ppc * 32 * CI);
-  if (L.total > 48 * 1024)
-    cudaFuncSetAttribute(agg_bwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  const size_t smem = L.total + (FAM == CL3D_FAM_PSEUDOGRID ? pg_bwd_extra_floats(CI) * sizeof(float) : 0);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(agg_bwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(grid_x, nchunks);
-  agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, smem, stream>>>(a);
   CL3D_LAUNCHED(1);
   return check_launch("agg_bwd_kernel");
 }
@@ -535,7 +856,35 @@ static int pick_ci(int family, int Cp) {
     default: return FN<FAM, 3>(__VA_ARGS__);               \
   }
 
+template <int PI>
+static int launch_sincos(const AggArgs& a, bool bwd, int grid_x, cudaStream_t stream) {
+  const int npairs = a.C / 2;
+  const SmemLayout L = smem_layout(2 * 32 * PI, 0);
+  dim3 grid(grid_x, ceil_div(npairs, 32 * PI));
+  if (!bwd) {
+    if (L.total > 48 * 1024)
+      cudaFuncSetAttribute(sincos_fwd_kernel<PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    sincos_fwd_kernel<PI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  } else {
+    if (L.total > 48 * 1024)
+      cudaFuncSetAttribute(sincos_bwd_kernel<PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    sincos_bwd_kernel<PI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  }
+  CL3D_LAUNCHED(1);
+  return check_launch("sincos kernel");
+}
+static int dispatch_sincos(const AggArgs& a, bool bwd, int grid_x, cudaStream_t s) {
+  int pi = ceil_div(a.C / 2, 32);
+  if (pi > 3) pi = 3;
+  switch (pi) {
+    case 1: return launch_sincos<1>(a, bwd, grid_x, s);
+    case 2: return launch_sincos<2>(a, bwd, grid_x, s);
+    default: return launch_sincos<3>(a, bwd, grid_x, s);
+  }
+}
+
 static int dispatch_fwd(int family, int ci, const AggArgs& a, cudaStream_t s) {
+  if (family == CL3D_FAM_POSPOOL_SINCOS) return dispatch_sincos(a, false, a.ntiles, s);
   switch (family) {
     case CL3D_FAM_POSPOOL_XYZ: DISPATCH_CI(launch_fwd, CL3D_FAM_POSPOOL_XYZ, a, s)
     case CL3D_FAM_POSPOOL_SINCOS: DISPATCH_CI(launch_fwd, CL3D_FAM_POSPOOL_SINCOS, a, s)
@@ -545,6 +894,7 @@ static int dispatch_fwd(int family, int ci, const AggArgs& a, cudaStream_t s) {
   return CL3D_ERR_UNSUPPORTED;
 }
 static int dispatch_bwd(int family, int ci, const AggArgs& a, int gx, cudaStream_t s) {
+  if (family == CL3D_FAM_POSPOOL_SINCOS) return dispatch_sincos(a, true, gx, s);
   switch (family) {
     case CL3D_FAM_POSPOOL_XYZ: DISPATCH_CI(launch_bwd, CL3D_FAM_POSPOOL_XYZ, a, gx, s)
     case CL3D_FAM_POSPOOL_SINCOS: DISPATCH_CI(launch_bwd, CL3D_FAM_POSPOOL_SINCOS, a, gx, s)
@@ -597,6 +947,7 @@ static void fill_common(AggArgs& a, int B, int N, int M, int K, int C, float rad
   a.influence = influence;
   a.inv_radius = 1.0f / radius;
   a.extent = extent;
+  a.inv_extent = 1.0f / extent;
 }
 
 extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, const float* query_xyz,
