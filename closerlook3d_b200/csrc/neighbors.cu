@@ -681,7 +681,9 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
   const bool brute = algo == CL3D_BQ_BRUTE || (algo == CL3D_BQ_AUTO && N <= kBruteMaxN);
   if (brute) {
     size_t smem = (size_t)((N + 31) & ~31) * 16 + (size_t)kBQWarps * cap3k * 8 + (size_t)kBQWarps * K * 4;
-    const int qpc = 64;  // queries per CTA (8 per warp): amortises the cloud load, keeps >= 148 CTAs at c2
+    // queries per CTA: 64 (8 per warp) amortises the cloud load; fewer when that would leave SMs idle
+    int qpc = 64;
+    while (qpc > 8 && (long long)B * ceil_div(M, qpc) < 6LL * sm_count()) qpc >>= 1;
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(ball_query_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -15,11 +15,11 @@
 // out = relu(sc*y_sel + sh).
 //
 // backward (BatchNorm2d backward is dense over B*M*K:  dy = sc*[k==k*]*dz - c1 - c2*(y - mean)):
-//   pwmlp_bwd_stats_kernel  sum dz, sum dz*yhat                                  (elementwise + reduce)
+//   pwmlp_bwd_stats_kernel  sum dz, sum dz*yhat, and sc*dz written point-major     (elementwise + reduce)
 //   pwmlp_bwd_dense_kernel  support-major over the all-slots CSR lists: the dense part of d/dbv needs only
 //                           cnt_j and sum_e a'[q_e]  -> one row gather, 2 instructions per element, no atomics
-//   pwmlp_bwd_sparse_kernel query-major, no K loop: d/da' in closed form from the saved S, the arg-max slot's
-//                           sc*dz and d/dA[j_0] as one fp32 red.add row each, d/dWp partials
+//   pwmlp_bwd_query_kernel  thread per (query, 4 channels), no K loop: d/da' in closed form from the saved S,
+//                           d/dA[j_0] as one red.global.add.v4.f32, the arg-max slot's sc*dz, d/dWp partials
 #include "common.cuh"
 
 namespace cl3d {
@@ -49,6 +49,7 @@ struct PwArgs {
   const int* csr_off;        // (B,N+1)   all-slots lists
   const int* csr_ent;        // (B,M*K)
   float* grad_ab_pm;         // (B,N,2*Cop)
+  const float* dzs_pm;       // (B,M,Cop) sc*dz, point-major
   int B, N, M, K, Cout, Cop;
   float inv_radius, inv_count;
   int ntiles;
@@ -89,6 +90,14 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_fwd_kernel(const PwArgs a
   const unsigned rstride = 2u * (unsigned)a.Cop;
   const float fK = (float)a.K;
 
+  // neighbour indices of the NEXT query are fetched while the current one is processed (K <= 64: two per lane)
+  const bool pre_ok = a.K <= 64;
+  int pre0 = 0, pre1 = 0;
+  if (pre_ok && q0 + warp < a.M) {
+    const int* ip = a.idx + ((size_t)b * a.M + q0 + warp) * a.K;
+    if (lane < a.K) pre0 = ip[lane];
+    if (lane + 32 < a.K) pre1 = ip[lane + 32];
+  }
   for (int ql = warp; ql < kPWTile; ql += kPWWarps) {
     const int q = q0 + ql;
     float ys[CI];
@@ -96,7 +105,17 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_fwd_kernel(const PwArgs a
     for (int i = 0; i < CI; ++i) ys[i] = 0.f;
     if (q < a.M) {
       const size_t gq = (size_t)b * a.M + q;
-      for (int k = lane; k < a.K; k += 32) s_idx[k] = (int)((unsigned)a.idx[gq * a.K + k] * rstride);  // row offsets
+      if (pre_ok) {
+        if (lane < a.K) s_idx[lane] = (int)((unsigned)pre0 * rstride);
+        if (lane + 32 < a.K) s_idx[lane + 32] = (int)((unsigned)pre1 * rstride);
+        if (ql + kPWWarps < kPWTile && q + kPWWarps < a.M) {
+          const int* ip = a.idx + (gq + kPWWarps) * a.K;
+          if (lane < a.K) pre0 = ip[lane];
+          if (lane + 32 < a.K) pre1 = ip[lane + 32];
+        }
+      } else {
+        for (int k = lane; k < a.K; k += 32) s_idx[k] = (int)((unsigned)a.idx[gq * a.K + k] * rstride);  // row offsets
+      }
       // a' = A[j_0] - Wp q/r      (slot 0 = nearest neighbour, reference :290)
       const float qx = __fmul_rn(a.query_xyz[gq * 3 + 0], a.inv_radius), qy = __fmul_rn(a.query_xyz[gq * 3 + 1], a.inv_radius),
                   qz = __fmul_rn(a.query_xyz[gq * 3 + 2], a.inv_radius);
@@ -212,28 +231,41 @@ __global__ void __launch_bounds__(256) pwmlp_out_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) pwmlp_bwd_stats_kernel(const float* __restrict__ grad_out,
                                                               const float* __restrict__ out,
                                                               const float* __restrict__ ysel,
-                                                              const float* __restrict__ stats, int C, int M,
-                                                              float* __restrict__ partial) {
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, int C, int Cop, int M,
+                                                              float* __restrict__ partial,
+                                                              float* __restrict__ dzs_pm /*(B,M,Cop): sc*dz*/) {
+  extern __shared__ float s_tile[];  // [32][Cop + 1]
   const int tiles_per_cloud = (M + kPWTile - 1) / kPWTile;
   const int b = blockIdx.x / tiles_per_cloud;
-  const int q = (blockIdx.x % tiles_per_cloud) * kPWTile + (threadIdx.x & 31);
+  const int q0 = (blockIdx.x % tiles_per_cloud) * kPWTile;
+  const int q = q0 + (threadIdx.x & 31);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = warp; c < C; c += 8) {
-    float dz = 0.f, dzy = 0.f;
-    if (q < M) {
+  for (int c = warp; c < Cop; c += 8) {
+    float dz = 0.f, dzy = 0.f, sc = 0.f;
+    if (c < C && q < M) {
       const size_t o = ((size_t)b * C + c) * M + q;
       dz = out[o] > 0.f ? grad_out[o] : 0.f;
       dzy = dz * ((ysel[o] - stats[c]) * stats[C + c]);
+      sc = stats[C + c] * gamma[c];
     }
-    const float t1 = warp_sum(dz), t2 = warp_sum(dzy);
-    if (lane == 0) {
-      partial[((size_t)blockIdx.x * 2 + 0) * C + c] = t2;  // -> dgamma = sum dz*yhat
-      partial[((size_t)blockIdx.x * 2 + 1) * C + c] = t1;  // -> dbeta  = sum dz
+    s_tile[(size_t)lane * (Cop + 1) + c] = sc * dz;
+    if (c < C) {
+      const float t1 = warp_sum(dz), t2 = warp_sum(dzy);
+      if (lane == 0) {
+        partial[((size_t)blockIdx.x * 2 + 0) * C + c] = t2;  // -> dgamma = sum dz*yhat
+        partial[((size_t)blockIdx.x * 2 + 1) * C + c] = t1;  // -> dbeta  = sum dz
+      }
     }
   }
+  __syncthreads();
+  const int nq = min(kPWTile, M - q0);
+  float* dst = dzs_pm + ((size_t)b * M + q0) * Cop;
+  for (int e = threadIdx.x; e < nq * Cop; e += blockDim.x) dst[e] = s_tile[(size_t)(e / Cop) * (Cop + 1) + e % Cop];
 }
 
-// dense part, support-major: grad_T[j] = sgn * ( -cnt*c1 - c2*(sum_e a'[q_e] + cnt*(bv[j] - mean)) ), grad_A[j] = 0
+// Support-major pass over the all-slots CSR lists of point j (no float atomics): dense part of d/dbv
+//   grad_T[j] = sgn * ( -cnt*c1 - c2*(sum_e a'[q_e] + cnt*(bv[j] - mean)) ),   grad_A[j] = 0
 template <int CI>
 __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_dense_kernel(const PwArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -295,7 +327,7 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_dense_kernel(const Pw
       float* grow = a.grad_ab_pm + ((size_t)b * a.N + j) * 2 * a.Cop;
 #pragma unroll
       for (int i = 0; i < CI; ++i) {
-        if (lane + 32 * i < chunkC) {
+        if (okc[i]) {
           const float bv = sg[i] * __ldg(trow + 32 * i);
           const float dbv = -cnt * c1[i] - c2[i] * (acc[i] + cnt * (bv - mean[i]));
           grow[a.Cop + c0 + lane + 32 * i] = (c0 + lane + 32 * i < a.Cout) ? sg[i] * dbv : 0.f;
@@ -306,87 +338,76 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_dense_kernel(const Pw
   }
 }
 
-// sparse part, query-major (no K loop)
-template <int CI>
-__global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_sparse_kernel(const PwArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.y * 32 * CI;
-  const int chunkC = min(32 * CI, a.Cop - c0);
-  float* s_dz = reinterpret_cast<float*>(smem);            // [chunk][tile+1]: sc * dz
-  float* s_red = s_dz + (size_t)32 * CI * (kPWTile + 1);   // [warps][3][chunk]
-  const int tiles_per_cloud = (a.M + kPWTile - 1) / kPWTile;
-  const int b = blockIdx.x / tiles_per_cloud;
-  const int q0 = (blockIdx.x % tiles_per_cloud) * kPWTile;
-  {
-    const int q = q0 + lane;
-    for (int cl = warp; cl < 32 * CI; cl += kPWWarps) {
-      const int c = c0 + cl;
-      float v = 0.f;
-      if (c < a.Cout && q < a.M) {
-        const size_t o = ((size_t)b * a.Cout + c) * a.M + q;
-        v = a.out[o] > 0.f ? a.grad_out[o] * (a.stats[a.Cout + c] * a.gamma[c]) : 0.f;
-      }
-      s_dz[(size_t)cl * (kPWTile + 1) + lane] = v;
-    }
-  }
-  __syncthreads();
-  float c1[CI], c2[CI], mean[CI], sg[CI], dwx[CI], dwy[CI], dwz[CI];
+// Query-side pass, no K loop.  Thread (x, y): x = one group of 4 consecutive channels, y = a query lane; every
+// thread walks kPWQPT queries so that d/dWp accumulates in registers (deterministic, no shared-memory atomics):
+//   da'[q] = sum_k dy[q,k] = sc*dz - K*c1 - c2*(K*(a' - mean) + S)      (closed form from the saved S)
+//   grad_A[j_0(q)] += da'      one 16-byte vector reduction (red.global.add.v4.f32) per (query, 4 channels)
+//   grad_T[idx[q][k*]] += sgn*sc*dz  at the arg-max slot of each channel (scalar red.add, non-zero only)
+//   d/dWp -= da' (x) q/r      per-CTA partial (gridDim.x, 3, Cout), reduced afterwards in a fixed order
+constexpr int kPWQPT = 8;  // queries per thread
+__global__ void __launch_bounds__(256) pwmlp_bwd_query_kernel(const PwArgs a, long long nqueries /* B*M */) {
+  extern __shared__ float s_dw[];  // [ny][3][Cop]
+  const int nx = a.Cop >> 2, ny = blockDim.x / nx;
+  const int x = threadIdx.x % nx, y = threadIdx.x / nx;
+  const int c4 = x * 4;
+  float c1[4], c2[4], mean[4], sg[4], dw[3][4];
 #pragma unroll
-  for (int i = 0; i < CI; ++i) {
-    const int c = c0 + lane + 32 * i;
+  for (int t = 0; t < 4; ++t) {
+    const int c = c4 + t;
     const bool ok = c < a.Cout;
     const float invstd = ok ? a.stats[a.Cout + c] : 0.f;
     const float sc = ok ? invstd * a.gamma[c] : 0.f;
-    mean[i] = ok ? a.stats[c] : 0.f;
-    c1[i] = ok ? sc * a.dgb[a.Cout + c] * a.inv_count : 0.f;
-    c2[i] = ok ? sc * invstd * a.dgb[c] * a.inv_count : 0.f;
-    sg[i] = ok ? a.sgn[c] : 1.f;
-    dwx[i] = dwy[i] = dwz[i] = 0.f;
+    mean[t] = ok ? a.stats[c] : 0.f;
+    c1[t] = ok ? sc * a.dgb[a.Cout + c] * a.inv_count : 0.f;
+    c2[t] = ok ? sc * invstd * a.dgb[c] * a.inv_count : 0.f;
+    sg[t] = ok ? a.sgn[c] : 1.f;
+    dw[0][t] = dw[1][t] = dw[2][t] = 0.f;
   }
-  float* gab = a.grad_ab_pm + (size_t)b * a.N * 2 * a.Cop;
   const float fK = (float)a.K;
-  for (int ql = warp; ql < kPWTile; ql += kPWWarps) {
-    const int q = q0 + ql;
-    if (q >= a.M) continue;
-    const size_t gq = (size_t)b * a.M + q;
-    const int* irow = a.idx + gq * a.K;
-    const int j0 = irow[0];
-    const float qx = __fmul_rn(a.query_xyz[gq * 3 + 0], a.inv_radius), qy = __fmul_rn(a.query_xyz[gq * 3 + 1], a.inv_radius),
-                qz = __fmul_rn(a.query_xyz[gq * 3 + 2], a.inv_radius);
+  {
+    const long long qbase = (long long)blockIdx.x * ny * kPWQPT;
+#pragma unroll 2
+    for (int it = 0; it < kPWQPT; ++it) {
+      const long long gq = qbase + (long long)it * ny + y;  // b*M + q
+      if (gq >= nqueries) break;
+      const long long b = gq / a.M;
+      const size_t o = (size_t)gq * a.Cop + c4;
+      const float4 ap = *reinterpret_cast<const float4*>(a.aq + o);
+      const float4 sb = *reinterpret_cast<const float4*>(a.sq + o);
+      const float4 dz = *reinterpret_cast<const float4*>(a.dzs_pm + o);
+      const uchar4 ks = *reinterpret_cast<const uchar4*>(a.karg + o);
+      const int* irow = a.idx + gq * a.K;
+      const int j0 = irow[0];
+      const float qx = __fmul_rn(a.query_xyz[gq * 3 + 0], a.inv_radius), qy = __fmul_rn(a.query_xyz[gq * 3 + 1], a.inv_radius),
+                  qz = __fmul_rn(a.query_xyz[gq * 3 + 2], a.inv_radius);
+      const float apv[4] = {ap.x, ap.y, ap.z, ap.w}, sbv[4] = {sb.x, sb.y, sb.z, sb.w}, dzv[4] = {dz.x, dz.y, dz.z, dz.w};
+      const int ksv[4] = {ks.x, ks.y, ks.z, ks.w};
+      float* gab = a.grad_ab_pm + (size_t)b * a.N * 2 * a.Cop;
+      float da[4];
 #pragma unroll
-    for (int i = 0; i < CI; ++i) {
-      const int cl = lane + 32 * i;
-      if (c0 + cl < a.Cout) {
-        const size_t o = gq * a.Cop + c0 + cl;
-        const float dzs = s_dz[(size_t)cl * (kPWTile + 1) + ql];
-        const float ap = a.aq[o], Sb = a.sq[o];
-        const int ks = a.karg[o];
-        // d/da' = sum_k dy = sc*dz - K*c1 - c2*(K*(a' - mean) + S)
-        const float da = dzs - fK * c1[i] - c2[i] * fmaf(fK, ap - mean[i], Sb);
-        atomicAdd(gab + (size_t)j0 * 2 * a.Cop + c0 + cl, da);                               // d/dA[j_0]
-        if (dzs != 0.f) atomicAdd(gab + (size_t)irow[ks] * 2 * a.Cop + a.Cop + c0 + cl, sg[i] * dzs);  // d/dT[j_k*]
-        dwx[i] = fmaf(-da, qx, dwx[i]);  // a' = A - Wp q/r
-        dwy[i] = fmaf(-da, qy, dwy[i]);
-        dwz[i] = fmaf(-da, qz, dwz[i]);
+      for (int t = 0; t < 4; ++t) {
+        da[t] = (c4 + t < a.Cout) ? dzv[t] - fK * c1[t] - c2[t] * fmaf(fK, apv[t] - mean[t], sbv[t]) : 0.f;
+        if (dzv[t] != 0.f && c4 + t < a.Cout)
+          atomicAdd(gab + (size_t)irow[ksv[t]] * 2 * a.Cop + a.Cop + c4 + t, sg[t] * dzv[t]);
+        dw[0][t] = fmaf(-da[t], qx, dw[0][t]);
+        dw[1][t] = fmaf(-da[t], qy, dw[1][t]);
+        dw[2][t] = fmaf(-da[t], qz, dw[2][t]);
       }
+      float* pa = gab + (size_t)j0 * 2 * a.Cop + c4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pa), "f"(da[0]), "f"(da[1]), "f"(da[2]), "f"(da[3])
+                   : "memory");
     }
-  }
 #pragma unroll
-  for (int i = 0; i < CI; ++i) {
-    s_red[((size_t)warp * 3 + 0) * 32 * CI + lane + 32 * i] = dwx[i];
-    s_red[((size_t)warp * 3 + 1) * 32 * CI + lane + 32 * i] = dwy[i];
-    s_red[((size_t)warp * 3 + 2) * 32 * CI + lane + 32 * i] = dwz[i];
+    for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s_dw[((size_t)y * 3 + s3) * a.Cop + c4 + t] = dw[s3][t];
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 3 * 32 * CI; e += blockDim.x) {
-    const int s = e / (32 * CI), cl = e % (32 * CI);
-    const int c = c0 + cl;
-    if (c >= a.Cout) continue;
+  for (int e = threadIdx.x; e < 3 * a.Cout; e += blockDim.x) {
+    const int s3 = e / a.Cout, c = e % a.Cout;
     float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < kPWWarps; ++w) t += s_red[((size_t)w * 3 + s) * 32 * CI + cl];
-    a.partial[((size_t)blockIdx.x * 3 + s) * a.Cout + c] = t;
+    for (int yy = 0; yy < ny; ++yy) t += s_dw[((size_t)yy * 3 + s3) * a.Cop + c];
+    a.partial[(size_t)blockIdx.x * 3 * a.Cout + e] = t;
   }
 }
 
@@ -473,19 +494,21 @@ static int launch_pw_fwd(const PwArgs& a, cudaStream_t stream) {
   return check_launch("pwmlp_fwd_kernel");
 }
 template <int CI>
-static int launch_pw_bwd(const PwArgs& a, int ntiles_n, cudaStream_t stream) {
+static int launch_pw_bwd(const PwArgs& a, int ntiles_n, int gx, cudaStream_t stream) {
   PwArgs d = a;
   d.ntiles = ntiles_n;
-  int gx = sm_count() * 4;
-  if (gx > ntiles_n) gx = ntiles_n;
   pwmlp_bwd_dense_kernel<CI><<<dim3(gx, ceil_div(a.Cop, 32 * CI)), kPWWarps * 32, 0, stream>>>(d);
   CL3D_LAUNCHED(1);
-  const size_t smem = (size_t)32 * CI * (kPWTile + 1) * 4 + (size_t)kPWWarps * 3 * 32 * CI * 4;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(pwmlp_bwd_sparse_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  pwmlp_bwd_sparse_kernel<CI><<<dim3(a.ntiles, ceil_div(a.Cop, 32 * CI)), kPWWarps * 32, smem, stream>>>(a);
-  CL3D_LAUNCHED(1);
-  return check_launch("pwmlp_bwd kernels");
+  return check_launch("pwmlp_bwd_dense_kernel");
+}
+
+static int pw_dense_grid(int ntiles_n) {
+  int gx = sm_count() * 4;
+  return gx > ntiles_n ? ntiles_n : gx;
+}
+static int pw_query_grid(int B, int M, int Cop) {
+  const int ny = 256 / (Cop / 4) > 0 ? 256 / (Cop / 4) : 1;
+  return (int)(((long long)B * M + (long long)ny * kPWQPT - 1) / ((long long)ny * kPWQPT));
 }
 
 }  // namespace cl3d
@@ -556,21 +579,40 @@ extern "C" int cl3d_pwmlp_fwd_out(const float* ysel, const float* save_stats, co
   return check_launch("pwmlp_out_kernel");
 }
 
+extern "C" size_t cl3d_pwmlp_bwd_scratch_floats(int B, int N, int M, int Cout) {
+  const int Cop = padded_channels(Cout);
+  (void)N;
+  const size_t ntm = (size_t)B * ceil_div(M, kPWTile), gq = (size_t)pw_query_grid(B, M, Cop);
+  const size_t part = (ntm * 2 > gq * 3 ? ntm * 2 : gq * 3) * (size_t)Cout;
+  return part + (size_t)B * M * Cop + 64;
+}
+
 extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, const float* wp,
                               const float* sgn, const float* query_xyz, const int* idx, const int* csr_off,
                               const int* csr_ent, const float* ysel, const float* aq, const float* sq,
                               const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
-                              int M, int K, int Cout, float radius, float* partial, float* dgamma_dbeta,
+                              int M, int K, int Cout, float radius, float* scratch, float* dgamma_dbeta,
                               float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   CL3D_REQUIRE(grad_out && out && ab_pm && wp && sgn && query_xyz && idx && csr_off && csr_ent && ysel && aq && sq &&
-                   karg && save_stats && gamma && partial && dgamma_dbeta && grad_ab_pm && grad_wp,
+                   karg && save_stats && gamma && scratch && dgamma_dbeta && grad_ab_pm && grad_wp,
                "cl3d_pwmlp_bwd: null pointer");
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 1 && K >= 1 && K <= 255 && Cout >= 1, "cl3d_pwmlp_bwd: bad sizes");
   if (B == 0) return CL3D_OK;
   const int ntiles = B * ceil_div(M, kPWTile);
+  const int ntn = B * ceil_div(N, kPWTile);
+  const int gx = pw_dense_grid(ntn);
   const int Cop = padded_channels(Cout);
-  pwmlp_bwd_stats_kernel<<<ntiles, 256, 0, stream>>>(grad_out, out, ysel, save_stats, Cout, M, partial);
+  // scratch = [ partials (max(ntiles*2, gx*3) * Cout) | dzs_pm (B*M*Cop) ]
+  const int gqy = pw_query_grid(B, M, Cop);
+  const size_t part = ((size_t)ntiles * 2 > (size_t)gqy * 3 ? (size_t)ntiles * 2 : (size_t)gqy * 3) * (size_t)Cout;
+  float* partial = scratch;
+  float* dzs_pm = scratch + ((part + 63) / 64) * 64;
+  const size_t smem_s = (size_t)kPWTile * (Cop + 1) * sizeof(float);
+  if (smem_s > 48 * 1024)
+    cudaFuncSetAttribute(pwmlp_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+  pwmlp_bwd_stats_kernel<<<ntiles, 256, smem_s, stream>>>(grad_out, out, ysel, save_stats, gamma, Cout, Cop, M, partial,
+                                                          dzs_pm);
   CL3D_LAUNCHED(1);
   int rc = cl3d_reduce_partials(partial, ntiles, 2 * Cout, dgamma_dbeta, stream_);  // (dgamma, dbeta)
   if (rc) return rc;
@@ -582,17 +624,23 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   a.grad_out = grad_out; a.out = out; a.stats = save_stats; a.gamma = gamma; a.dgb = dgamma_dbeta;
   a.csr_off = csr_off; a.csr_ent = csr_ent;
   a.grad_ab_pm = grad_ab_pm;
+  a.dzs_pm = dzs_pm;
   a.B = B; a.N = N; a.M = M; a.K = K; a.Cout = Cout; a.Cop = Cop;
   a.inv_radius = 1.0f / radius;
   a.inv_count = 1.0f / (float)((double)B * M * K);
   a.ntiles = ntiles;
-  const int ntn = B * ceil_div(N, kPWTile);
   switch (pw_ci(Cop)) {
-    case 1: rc = launch_pw_bwd<1>(a, ntn, stream); break;
-    case 2: rc = launch_pw_bwd<2>(a, ntn, stream); break;
-    case 3: rc = launch_pw_bwd<3>(a, ntn, stream); break;
-    default: rc = launch_pw_bwd<4>(a, ntn, stream); break;
+    case 1: rc = launch_pw_bwd<1>(a, ntn, gx, stream); break;
+    case 2: rc = launch_pw_bwd<2>(a, ntn, gx, stream); break;
+    case 3: rc = launch_pw_bwd<3>(a, ntn, gx, stream); break;
+    default: rc = launch_pw_bwd<4>(a, ntn, gx, stream); break;
   }
   if (rc) return rc;
-  return cl3d_reduce_partials(partial, ntiles, 3 * Cout, grad_wp, stream_);
+  CL3D_REQUIRE(Cop / 4 <= 256, "cl3d_pwmlp_bwd: Cout > 1024 unsupported");
+  const int ny = 256 / (Cop / 4);
+  pwmlp_bwd_query_kernel<<<gqy, ny * (Cop / 4), (size_t)ny * 3 * Cop * sizeof(float), stream>>>(a, (long long)B * M);
+  CL3D_LAUNCHED(1);
+  rc = check_launch("pwmlp_bwd_query_kernel");
+  if (rc) return rc;
+  return cl3d_reduce_partials(partial, gqy, 3 * Cout, grad_wp, stream_);
 }

@@ -272,7 +272,7 @@ def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, y
     Cout, M, K = out.shape[1], out.shape[2], idx.shape[2]
     L = _lib.lib()
     dev = out.device
-    partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 3, Cout, dtype=F32, device=dev)
+    partial = _empty_pm(1, 1, L.cl3d_pwmlp_bwd_scratch_floats(B, N, M, Cout), dev)  # partial sums + sc*dz rows
     dgb = torch.empty(2, Cout, dtype=F32, device=dev)
     grad_ab = torch.empty(B, N, C2, dtype=F32, device=dev)
     grad_wp = torch.empty(3, Cout, dtype=F32, device=dev)

@@ -55,13 +55,19 @@ class _FusedPointWiseMLP(Function):
                                                         off, ent, ysel, aq, sq, karg, stats, bn_weight, ctx.radius)
         P = B * N
         Cp = ops.padded_channels(C)
+        # the two products of the backward are independent: the weight gradient runs on the side stream
+        cur = torch.cuda.current_stream()
+        side = pt_utils._side_stream(grad_ab.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            # d/dwcat (2Cop x Cpa) = grad_AB^T (2Cop x P) @ fa (P x Cpa): long reduction -> split-K
+            splitk = max(1, min(256, P // 256))
+            gwcat = ops.sgemm(grad_ab, 1, 2 * Cop, fa_pm, Cpa, 1, 2 * Cop, Cpa, P, splitk=splitk)
+            gW = ops.pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout)
         # d/dfeat (point-major) = grad_AB (P x 2Cop) @ wcat[:, :Cp] (2Cop x Cp; columns >= C are unused)
         gf_pm = ops.sgemm(grad_ab, 2 * Cop, 1, wcat, Cpa, 1, P, Cp, 2 * Cop, ldc=Cp).view(B, N, Cp)
         grad_feat = ops.to_channel_major(gf_pm, C)
-        # d/dwcat (2Cop x (C+3)) = grad_AB^T (2Cop x P) @ fa (P x (C+3)): long reduction -> split-K
-        splitk = max(1, min(256, P // 256))
-        gwcat = ops.sgemm(grad_ab, 1, 2 * Cop, fa_pm, Cpa, 1, 2 * Cop, Cpa, P, splitk=splitk)
-        gW = ops.pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout)
+        cur.wait_stream(side)
         return grad_feat, gW, dgamma, dbeta, None, None, None, None, None
 
 

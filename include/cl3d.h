@@ -215,10 +215,12 @@ int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, l
  *             first arg-max slot (K <= 255); bn_partial (cl3d_agg_num_tiles(B,M), 2, Cout) -> cl3d_bn_finalize
  *             with count = B*M*K.
  * fwd_out   : out (B,Cout,M) = relu(sc*ysel + sh).
- * bwd       : csr_off/csr_ent = cl3d_build_csr over ALL K slots (ncount = K); partial = scratch
- *             (cl3d_agg_num_tiles(B,M), 3, Cout); dgamma_dbeta (2,Cout); grad_ab_pm (B,N,2*Cop) fully written
- *             (dense part stored, sparse part added with fp32 red.add); grad_wp (3,Cout) = the -sum da' (x) q/r
- *             part of d/dWp (the rest comes out of the weight-gradient product). */
+ * bwd       : csr_off/csr_ent = cl3d_build_csr over ALL K slots (ncount = K); scratch =
+ *             cl3d_pwmlp_bwd_scratch_floats(...) floats; dgamma_dbeta (2,Cout); grad_ab_pm (B,N,2*Cop) fully
+ *             written (dense part + d/dA stored by the support-major pass, arg-max hits added with fp32 red.add);
+ *             grad_wp (3,Cout) = the -sum da' (x) q/r part of d/dWp (the rest comes out of the weight-gradient
+ *             product). */
+size_t cl3d_pwmlp_bwd_scratch_floats(int B, int N, int M, int Cout);
 /* conv weight (Cout, 3+2C) = [Wp|Wc|Wr] + BN gamma -> wcat (2*Cop, Cpa) (rows zero-padded to Cpa), wp (Cout,3),
  * sgn (Cout); and back: d/dwcat (2*Cop, Cpa) + grad_wp (3,Cout) -> d/d(conv weight) (Cout, 3+2C). */
 int cl3d_pwmlp_prep_weights(const float* conv_weight, const float* gamma, int C, int Cout, float* wcat,
@@ -236,7 +238,7 @@ int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, 
                    const float* sgn, const float* query_xyz, const int* idx, const int* csr_off,
                    const int* csr_ent, const float* ysel, const float* aq, const float* sq,
                    const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
-                   int M, int K, int Cout, float radius, float* partial, float* dgamma_dbeta,
+                   int M, int K, int Cout, float radius, float* scratch, float* dgamma_dbeta,
                    float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream);
 
 #ifdef __cplusplus
