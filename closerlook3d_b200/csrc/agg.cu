@@ -598,12 +598,14 @@ __device__ __forceinline__ void sincos_small(float x, float& sn, float& cs) {
   cs = ((q + 1) & 2) ? -c0 : c0;
 }
 
-// n / d with a precomputed reciprocal: one Newton correction on the quotient (correctly rounded except in rare
-// double-rounding cases; d >= 1 here, no overflow / denormals)
+// n / d, correctly rounded, with a precomputed correctly-rounded reciprocal: two residual corrections on the
+// quotient (Markstein).  d >= 1 and |n| ~ 1e2 here: no overflow / denormals.  One ulp of the argument is
+// 7.6e-6 rad at |arg| ~ 100, so the division has to be exact to stay inside the 1e-5 parity bar.
 __device__ __forceinline__ float div_by(float n, float d, float rcp_d) {
-  const float q0 = n * rcp_d;
-  const float r = __fmaf_rn(-d, q0, n);
-  return __fmaf_rn(r, rcp_d, q0);
+  float q = n * rcp_d;
+  q = __fmaf_rn(__fmaf_rn(-d, q, n), rcp_d, q);
+  q = __fmaf_rn(__fmaf_rn(-d, q, n), rcp_d, q);
+  return q;
 }
 
 template <int PI, bool BWD>

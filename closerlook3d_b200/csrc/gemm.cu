@@ -232,11 +232,11 @@ extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const 
     }
     partial = (float*)workspace;
   }
-  // columns per thread: spread N over the fewest 128-wide column tiles, then round each tile up to 16*TN
-  const int nct = ceil_div(N, 128);
+  // columns per thread: spread N over the fewest 144-wide column tiles, then round each tile up to 16*TN
+  const int nct = ceil_div(N, 144);
   int tn = ceil_div(ceil_div(N, nct), 16);
   if (tn < 1) tn = 1;
-  if (tn > 8) tn = 8;
+  if (tn > 9) tn = 9;
   dim3 grid(ceil_div(N, 16 * tn), ceil_div(M, kBM), splitk);
   switch (tn) {
     case 1: launch_sgemm<1>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
@@ -246,7 +246,8 @@ extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const 
     case 5: launch_sgemm<5>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
     case 6: launch_sgemm<6>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
     case 7: launch_sgemm<7>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
-    default: launch_sgemm<8>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    case 8: launch_sgemm<8>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
+    default: launch_sgemm<9>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
   }
   if (splitk > 1) {
     const long long total = (long long)M * N;

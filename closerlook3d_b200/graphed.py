@@ -35,6 +35,10 @@ class GraphedStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        try:  # parameters were created on the default stream; the captured backward accumulates on the capture stream
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except Exception:
+            pass
         self.graph = torch.cuda.CUDAGraph()
         self.features.grad = None
         for p in self.params:

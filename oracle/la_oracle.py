@@ -41,6 +41,15 @@ def make_grouping(ext):
     return _Group.apply
 
 
+# torch's CUDA kernel for `tensor / python_scalar` multiplies by the fp32 reciprocal of the scalar
+# (aten/src/ATen/native/cuda/BinaryDivTrueKernel.cu: "compute a * reciprocal(b)"), the CPU kernel divides.  The
+# reference's `grouped_xyz /= self.radius` (pt_utils.py:129) therefore differs by up to 1 ulp between its GPU path
+# and a CPU run -- harmless, except that PosPool sin_cos evaluates sin(100 * dp / dim): one ulp of dp is ~1e-5 rad
+# there.  GPU parity tests set this flag so that the oracle follows the reference's GPU arithmetic; the pins
+# against the unmodified reference modules on CPU (tests/test_oracle_cpu.py, tests/golden) keep it False.
+GPU_SCALAR_DIVISION = False
+
+
 def query_and_group(ext, query_xyz, support_xyz, query_mask, support_mask, features, radius, nsample,
                     normalize_xyz):
     """pt_utils.py:121-144 with use_xyz=False, ret_grouped_xyz=True (the only way LA uses it).
@@ -53,7 +62,11 @@ def query_and_group(ext, query_xyz, support_xyz, query_mask, support_mask, featu
     grouped_xyz = group(xyz_t, idx)
     grouped_xyz = grouped_xyz - query_xyz.transpose(1, 2).unsqueeze(-1)      # :127
     if normalize_xyz:
-        grouped_xyz = grouped_xyz / radius                                    # :128-129 true division by float(radius)
+        if GPU_SCALAR_DIVISION:
+            inv = (torch.ones((), dtype=torch.float32) / torch.tensor(radius, dtype=torch.float32)).item()
+            grouped_xyz = grouped_xyz * inv                                   # what the CUDA kernel computes
+        else:
+            grouped_xyz = grouped_xyz / radius                                # :128-129 true division by float(radius)
     grouped_features = group(features, idx) if features is not None else None
     return grouped_features, grouped_xyz, idx_mask, idx
 

@@ -59,7 +59,8 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
         qm[:, M - M // 8:] = 0
     gout = torch.randn(B, C, q.shape[1], generator=torch.Generator().manual_seed(seed + 2))
 
-    # ---- forward on both sides
+    # ---- forward on both sides (the oracle follows the reference's GPU arithmetic for `/= radius`, see la_oracle)
+    la_oracle.GPU_SCALAR_DIVISION = True
     orc = la_oracle.OracleLocalAggregation(oracle_ext, la_type, C, C, r, K, cfg, sd)
     orc.training = train
     f_ref = feats.clone().requires_grad_(True)
@@ -71,6 +72,7 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     # The final ReLU makes the gradient discontinuous at 0: an output that is +4e-6 on one side and 0 on the
     # other is inside the output tolerance but flips a whole BN channel's gradient.  Such elements (a handful
     # per million) get zero upstream gradient on BOTH sides, so the comparison is well-posed.
+    la_oracle.GPU_SCALAR_DIVISION = False
     flips = (out.detach().cpu() > 0) != (o_ref.detach() > 0)
     assert int(flips.sum()) <= max(2, out.numel() // 100000), f"{int(flips.sum())} ReLU sign flips"
     gout = gout * (~flips)

@@ -1,0 +1,23 @@
+"""Turn an `ncu --set full` report into profiles/traffic.json entries:
+   python tools/ncu_traffic.py gpurun_out/prof.ncu-rep c2   -> prints {entry_point: dram bytes per launch}"""
+import csv, json, subprocess, sys, collections
+rep, cfg = sys.argv[1], sys.argv[2]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h, units = rows[0], rows[1]
+ki, ri, wi, ti = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+MAP = [("sgemm", "cl3d_sgemm"), ("splitk_reduce", "cl3d_sgemm"), ("ball_query", "cl3d_ball_query_algo"), ("grid_params", "cl3d_ball_query_algo"),
+       ("cell_", "cl3d_ball_query_algo"), ("zero_cells", "cl3d_ball_query_algo"), ("csr_", "cl3d_build_csr"),
+       ("pwmlp_fwd_kernel", "cl3d_pwmlp_fwd_stats"), ("pwmlp_out", "cl3d_pwmlp_fwd_out"), ("pwmlp_bwd", "cl3d_pwmlp_bwd"),
+       ("agg_fwd", "cl3d_agg_fwd"), ("sincos_fwd", "cl3d_agg_fwd"), ("agg_bwd", "cl3d_agg_bwd"), ("sincos_bwd", "cl3d_agg_bwd"),
+       ("bn_relu_fwd", "cl3d_bn_relu_fwd"), ("bn_relu_bwd", "cl3d_bn_relu_bwd"), ("bn_reduce2", "cl3d_bn_relu_bwd"),
+       ("bn_finalize", "cl3d_bn_finalize"), ("to_point_major", "cl3d_to_point_major"), ("to_channel_major", "cl3d_to_channel_major")]
+acc = collections.defaultdict(lambda: [0.0, 0, 0.0])
+for r in rows[2:]:
+    name = r[ki]
+    ent = next((e for k, e in MAP if k in name), None)
+    if ent is None: continue
+    b = float(r[ri]) * scale.get(units[ri], 1) + float(r[wi]) * scale.get(units[wi], 1)
+    acc[ent][0] += b; acc[ent][1] += 1; acc[ent][2] += float(r[ti])
+print(json.dumps({cfg: {e: {"dram_bytes_per_step": v[0], "kernels": v[1], "time_us_under_ncu": v[2]} for e, v in acc.items()}}, indent=1))
