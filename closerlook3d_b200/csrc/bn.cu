@@ -88,26 +88,49 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
   }
 }
 
-// backward pass 1: per tile (32 queries of one cloud) and channel: sum(gy), sum(gy * xhat)
+// Backward, tiles of 128 consecutive queries of one cloud: a warp owns a channel row segment (512 bytes, one
+// float4 per lane when M % 4 == 0), so both passes stream (B,C,M) with full-width, page-friendly accesses.
+constexpr int kBwdTile = 128;
+constexpr int kBwdCh = 32;  // channels staged per shared-memory transpose round in the apply pass
+
+__device__ __forceinline__ void load4(const float* __restrict__ p, int q, int M, bool vec, float (&v)[4]) {
+  if (vec && q + 3 < M) {
+    const float4 t = *reinterpret_cast<const float4*>(p + q);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = (q + t < M) ? p[q + t] : 0.f;
+  }
+}
+
+// pass 1: per tile and channel: sum(gy), sum(gy * xhat)
 __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float* __restrict__ grad_y,
                                                                 const float* __restrict__ x,
                                                                 const float* __restrict__ stats,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int C, int M,
                                                                 float* __restrict__ partial) {
-  const int tiles_per_cloud = (M + kBnTile - 1) / kBnTile;
+  const int tiles_per_cloud = (M + kBwdTile - 1) / kBwdTile;
   const int b = blockIdx.x / tiles_per_cloud;
-  const int q = (blockIdx.x % tiles_per_cloud) * kBnTile + (threadIdx.x & 31);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = (blockIdx.x % tiles_per_cloud) * kBwdTile + lane * 4;
+  const bool vec = (M & 3) == 0;
   for (int c = warp; c < C; c += 8) {
+    const size_t row = ((size_t)b * C + c) * M;
+    float xv[4], gv[4];
+    load4(x + row, q, M, vec, xv);
+    load4(grad_y + row, q, M, vec, gv);
+    const float mean = stats[c], invstd = stats[C + c], sc = invstd * gamma[c], sh = beta[c];
     float gy = 0.f, gx = 0.f;
-    if (q < M) {
-      const size_t o = ((size_t)b * C + c) * M + q;
-      const float xc = __fsub_rn(x[o], stats[c]);
-      const float xhat = xc * stats[C + c];
-      const float yv = __fmaf_rn(xc, stats[C + c] * gamma[c], beta[c]);  // bit-identical to the forward's y
-      gy = yv > 0.f ? grad_y[o] : 0.f;
-      gx = gy * xhat;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (q + t < M) {
+        const float xc = __fsub_rn(xv[t], mean);
+        const float yv = __fmaf_rn(xc, sc, sh);  // bit-identical to the forward's y
+        const float g = yv > 0.f ? gv[t] : 0.f;
+        gy += g;
+        gx = fmaf(g, xc * invstd, gx);
+      }
     }
     const float s1 = warp_sum(gy), s2 = warp_sum(gx);
     if (lane == 0) {
@@ -117,8 +140,8 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float* __r
   }
 }
 
-// backward pass 2: g = gamma*invstd*(gy - mean(gy) - xhat*mean(gy*xhat)) (training) or gamma*invstd*gy
-// (eval), written point-major (B,M,Cp) through a shared-memory transpose; padding channels = 0.
+// pass 2: g = gamma*invstd*(gy - mean(gy) - xhat*mean(gy*xhat)) (training) or gamma*invstd*gy (eval), written
+// point-major (B,M,Cp) through a shared-memory transpose, kBwdCh channels per round; padding channels = 0.
 __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ grad_y,
                                                                 const float* __restrict__ x,
                                                                 const float* __restrict__ stats,
@@ -127,34 +150,43 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ dgb, int C, int Cp, int M,
                                                                 float inv_count, int training,
                                                                 float* __restrict__ g_pm) {
-  extern __shared__ float s_tile[];  // [kBnTile][Cp + 1]
-  const int tiles_per_cloud = (M + kBnTile - 1) / kBnTile;
+  __shared__ float s_tile[kBwdTile][kBwdCh + 1];
+  const int tiles_per_cloud = (M + kBwdTile - 1) / kBwdTile;
   const int b = blockIdx.x / tiles_per_cloud;
-  const int q0 = (blockIdx.x % tiles_per_cloud) * kBnTile;
+  const int q0 = (blockIdx.x % tiles_per_cloud) * kBwdTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = q0 + lane;
-  for (int c = warp; c < Cp; c += 8) {
-    float g = 0.f;
-    if (c < C && q < M) {
-      const size_t o = ((size_t)b * C + c) * M + q;
-      const float invstd = stats[C + c];
-      const float xc = __fsub_rn(x[o], stats[c]);
-      const float xhat = xc * invstd;
-      const float yv = __fmaf_rn(xc, invstd * gamma[c], beta[c]);  // bit-identical to the forward's y
-      const float gy = yv > 0.f ? grad_y[o] : 0.f;
-      if (training)
-        g = gamma[c] * invstd * (gy - dgb[C + c] * inv_count - xhat * dgb[c] * inv_count);
-      else
-        g = gamma[c] * invstd * gy;
+  const int q = q0 + lane * 4;
+  const bool vec = (M & 3) == 0;
+  const int nq = min(kBwdTile, M - q0);
+  for (int cb = 0; cb < Cp; cb += kBwdCh) {
+    for (int cl = warp; cl < kBwdCh; cl += 8) {
+      const int c = cb + cl;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < C) {
+        const size_t row = ((size_t)b * C + c) * M;
+        float xv[4], gv[4];
+        load4(x + row, q, M, vec, xv);
+        load4(grad_y + row, q, M, vec, gv);
+        const float mean = stats[c], invstd = stats[C + c], ga = gamma[c], sc = invstd * ga, sh = beta[c];
+        const float mg = training ? dgb[C + c] * inv_count : 0.f, mgx = training ? dgb[c] * inv_count : 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float xc = __fsub_rn(xv[t], mean);
+          const float yv = __fmaf_rn(xc, sc, sh);
+          const float gy = yv > 0.f ? gv[t] : 0.f;
+          g[t] = sc * (gy - mg - xc * invstd * mgx);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s_tile[lane * 4 + t][cl] = g[t];
     }
-    s_tile[(size_t)lane * (Cp + 1) + c] = g;
-  }
-  __syncthreads();
-  const int nq = min(kBnTile, M - q0);
-  float* dst = g_pm + ((size_t)b * M + q0) * Cp;
-  for (int e = threadIdx.x; e < nq * Cp; e += blockDim.x) {
-    const int ql = e / Cp, c = e % Cp;
-    dst[e] = s_tile[(size_t)ql * (Cp + 1) + c];
+    __syncthreads();
+    const int ncb = min(kBwdCh, Cp - cb);
+    for (int e = threadIdx.x; e < nq * ncb; e += blockDim.x) {
+      const int ql = e / ncb, cl = e % ncb;
+      g_pm[((size_t)b * M + q0 + ql) * Cp + cb + cl] = s_tile[ql][cl];
+    }
+    __syncthreads();
   }
 }
 
@@ -235,14 +267,11 @@ extern "C" int cl3d_bn_relu_bwd(const float* grad_y, const float* x, const float
                "cl3d_bn_relu_bwd: null pointer");
   CL3D_REQUIRE(B >= 0 && C >= 1 && M >= 1, "cl3d_bn_relu_bwd: bad sizes");
   if (B == 0) return CL3D_OK;
-  const int ntiles = B * ceil_div(M, kBnTile);
+  const int ntiles = B * ceil_div(M, kBwdTile);  // <= cl3d_agg_num_tiles(B, M): the caller's partial buffer fits
   const int Cp = padded_channels(C);
   bn_relu_bwd_stats_kernel<<<ntiles, 256, 0, stream>>>(grad_y, x, save_stats, gamma, beta, C, M, partial); CL3D_LAUNCHED(1);
   bn_reduce2_kernel<<<ceil_div(C, 32), 1024, 0, stream>>>(partial, ntiles, C, dgamma_dbeta); CL3D_LAUNCHED(1);
-  const size_t smem = (size_t)kBnTile * (Cp + 1) * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(bn_relu_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  bn_relu_bwd_apply_kernel<<<ntiles, 256, smem, stream>>>(grad_y, x, save_stats, gamma, beta, dgamma_dbeta, C, Cp, M,
-                                                          1.0f / (float)((long long)B * M), training, g_pm); CL3D_LAUNCHED(1);
+  bn_relu_bwd_apply_kernel<<<ntiles, 256, 0, stream>>>(grad_y, x, save_stats, gamma, beta, dgamma_dbeta, C, Cp, M,
+                                                       1.0f / (float)((long long)B * M), training, g_pm); CL3D_LAUNCHED(1);
   return check_launch("bn_relu_bwd kernels");
 }
