@@ -66,3 +66,62 @@ class GraphedStep:
     def replay(self):
         self.graph.replay()
         return self.out
+
+
+class PipelinedTrainer:
+    """End-to-end stepping from HOST batches: two GraphedSteps (double-buffered static inputs) and a copy stream,
+    so the host->device copy of batch i+1 overlaps the replay of batch i; the step's result (sum of the output,
+    a stand-in for the loss) is copied back asynchronously and read one step later.  Every batch is still
+    copied, searched, aggregated and differentiated in full -- nothing is cached or skipped.
+
+        tr = PipelinedTrainer(module, example_xyz, example_mask, example_features, grad_out)
+        for host_batch in loader:            # pinned host tensors
+            prev_loss = tr.step(host_batch)  # returns the result of the PREVIOUS step (None on the first)
+        last = tr.flush()
+    """
+
+    def __init__(self, module, xyz, mask, features, grad_out, after_step=None):
+        self.slots = [GraphedStep(module, xyz, mask, features, grad_out) for _ in range(2)]
+        self.copy = torch.cuda.Stream()
+        self.after_step = after_step            # e.g. the gradient all-reduce + optimizer step
+        self.result_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]     # replay i finished (its buffers are free again)
+        self.loaded = [torch.cuda.Event(), torch.cuda.Event()]   # inputs of slot i are on the device
+        self.i = 0
+        self.pending = None
+        for e in self.done:
+            e.record()
+
+    def _issue_copy(self, slot, batch):
+        s = self.slots[slot]
+        self.copy.wait_event(self.done[slot])   # the previous replay on this slot no longer reads its inputs
+        with torch.cuda.stream(self.copy):
+            s.load(batch["xyz"], batch["mask"], batch["features"], non_blocking=True)
+            self.loaded[slot].record(self.copy)
+
+    def step(self, batch):
+        slot = self.i & 1
+        cur = torch.cuda.current_stream()
+        self._issue_copy(slot, batch)
+        cur.wait_event(self.loaded[slot])
+        out = self.slots[slot].replay()
+        if self.after_step is not None:
+            self.after_step(self.slots[slot])
+        self.result_host[slot].copy_(out.sum().reshape(1), non_blocking=True)  # D2H of the step's result
+        self.done[slot].record(cur)
+        prev = None
+        if self.pending is not None:
+            pslot = self.pending
+            self.done[pslot].synchronize()
+            prev = float(self.result_host[pslot][0])
+        self.pending = slot
+        self.i += 1
+        return prev
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        self.done[self.pending].synchronize()
+        v = float(self.result_host[self.pending][0])
+        self.pending = None
+        return v

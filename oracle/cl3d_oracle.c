@@ -42,6 +42,14 @@ static inline float ref_d2(float qx, float qy, float qz, float x, float y, float
   return t;
 }
 
+void cl3d_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int cl3d_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -38,6 +38,10 @@ def num_threads():
     return lib().cl3d_oracle_num_threads()
 
 
+def set_threads(n):
+    lib().cl3d_oracle_set_threads(int(n))
+
+
 def masked_ordered_ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample):
     """masked_ordered_ball_query.cpp:13-59 -> [idx (B,M,K) i32, idx_mask (B,M,K) i32]"""
     _chk(query_xyz, "query_xyz", torch.float32)
