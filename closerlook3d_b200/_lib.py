@@ -50,6 +50,7 @@ SIGNATURES = {
     "cl3d_bn_relu_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cl3d_sgemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "cl3d_sgemm": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _i, _vp, _ll, _i, _vp, _sz, _vp]),
+    "cl3d_sgemm_algo": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _i, _vp, _ll, _i, _vp, _sz, _i, _vp]),
     "cl3d_pwmlp_prep_weights": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "cl3d_pwmlp_weight_grad": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "cl3d_to_point_major_aug": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),

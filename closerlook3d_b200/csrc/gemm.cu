@@ -1,17 +1,22 @@
-// gemm.cu -- fp32 FMA GEMM with arbitrary element strides and optional split-K (sm_100a).
+// gemm.cu -- fp32 GEMM with arbitrary element strides and optional split-K (sm_100a).
 //
 // Used for the per-point products of the fused PointWiseMLP (see pwmlp.cu): the reference's per-neighbour
 // 1x1 conv over [dp; f_i; f_j - f_i] (/root/reference/pytorch/models/local_aggregation_operators.py:254-257,
-// 288-295) becomes ONE per-point product (B*N x (C+3)) x ((C+3) x 2*Cout), plus its two gradients.  These are
-// skinny problems (N, K ~ 75..150): far too small to fill a tcgen05 tile, and TF32/BF16 operands would break
-// the fp32 1e-5 parity bar, so they stay vectorised fp32 FMA (BASELINE.json north_star).
+// 288-295) becomes ONE per-point product (B*N x (C+3)) x ((C+3) x 2*Cout), plus its two gradients.
 //
 //   C[m][n] = sum_k A[m*sa_m + k*sa_k] * B[k*sb_k + n*sb_n]
-// CTA tile 128 x (16*TN), k tile 16, 256 threads, 8 x TN outputs per thread (TN chosen from N so that skinny
+//
+// Two implementations behind cl3d_sgemm_algo:
+//   CL3D_GEMM_TC3X (default): tcgen05 tensor cores, every operand split into two TF32 halves and three MMAs
+//     per product (gemm_tc.cuh) -- fp32-level accuracy, within the 1e-5 parity bar (BASELINE.json north_star);
+//   CL3D_GEMM_FFMA: the vectorised fp32 FMA kernel below (plain TF32/BF16 would break the parity bar).
+//
+// FFMA kernel: CTA tile 128 x (16*TN), k tile 16, 256 threads, 8 x TN outputs per thread (TN chosen from N so that skinny
 // outputs waste few columns), operands transposed into shared memory as [k][m] / [k][n] (LDS.128 for the A
 // fragment), next k tile prefetched into registers while the current one is multiplied.  With splitk > 1 the k
 // range is divided among gridDim.z CTAs that write partial tiles, reduced afterwards in a fixed order.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace cl3d {
 
@@ -171,21 +176,31 @@ __global__ void __launch_bounds__(256) sgemm_tiled_kernel(const float* __restric
   }
 }
 
+// Fixed-order split-K reduction: 32 outputs x 8 slices per CTA; slice j sums splits j, j+8, ... in double,
+// the 8 slice sums are combined in a fixed order.  C[m*sc_m + n*sc_n] for the partial element (m, n).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
-                                                            float* __restrict__ C, long long ldc) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)M * N) return;
+                                                            float* __restrict__ C, long long sc_m, long long sc_n) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long e = (long long)blockIdx.x * 32 + lane;
   const size_t stride = (size_t)M * N;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int s = 0;
-  for (; s + 4 <= splits; s += 4) {
-    a0 += (double)partial[(size_t)(s + 0) * stride + e];
-    a1 += (double)partial[(size_t)(s + 1) * stride + e];
-    a2 += (double)partial[(size_t)(s + 2) * stride + e];
-    a3 += (double)partial[(size_t)(s + 3) * stride + e];
+  double a0 = 0.0, a1 = 0.0;
+  if (e < (long long)stride) {
+    int s = slice;
+    for (; s + 8 < splits; s += 16) {
+      a0 += (double)partial[(size_t)s * stride + e];
+      a1 += (double)partial[(size_t)(s + 8) * stride + e];
+    }
+    if (s < splits) a0 += (double)partial[(size_t)s * stride + e];
   }
-  for (; s < splits; ++s) a0 += (double)partial[(size_t)s * stride + e];
-  C[(size_t)(e / N) * ldc + (e % N)] = (float)((a0 + a1) + (a2 + a3));
+  red[slice][lane] = a0 + a1;
+  __syncthreads();
+  if (slice == 0 && e < (long long)stride) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][lane];
+    C[(e / N) * sc_m + (e % N) * sc_n] = (float)t;
+  }
 }
 
 template <int TN>
@@ -213,25 +228,12 @@ extern "C" size_t cl3d_sgemm_workspace_bytes(int M, int N, int splitk) {
   return splitk > 1 ? sizeof(float) * (size_t)splitk * M * N : 0;
 }
 
-extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k,
-                          long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk, void* workspace,
-                          size_t workspace_bytes, cl3d_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  CL3D_REQUIRE(a && b && c && M >= 1 && N >= 1 && K >= 1 && ldc >= N, "cl3d_sgemm: bad arguments");
-  if (splitk < 1) splitk = 1;
-  if (splitk > K) splitk = K;
-  CL3D_REQUIRE(splitk <= 65535, "cl3d_sgemm: splitk too large");
+static int sgemm_ffma(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k, long long sb_n,
+                      int M, int N, int K, float* c, long long ldc, int splitk, float* partial, cudaStream_t stream) {
   int kps = ceil_div(K, splitk);
   kps = ceil_div(kps, kBK) * kBK;
   splitk = ceil_div(K, kps);
-  float* partial = nullptr;
-  if (splitk > 1) {
-    if (!workspace || workspace_bytes < cl3d_sgemm_workspace_bytes(M, N, splitk)) {
-      set_error("cl3d_sgemm: split-K workspace too small");
-      return CL3D_ERR_WORKSPACE;
-    }
-    partial = (float*)workspace;
-  }
+  if (splitk == 1) partial = nullptr;
   // columns per thread: spread N over the fewest 144-wide column tiles, then round each tile up to 16*TN
   const int nct = ceil_div(N, 144);
   int tn = ceil_div(ceil_div(N, nct), 16);
@@ -249,10 +251,88 @@ extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const 
     case 8: launch_sgemm<8>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
     default: launch_sgemm<9>(grid, stream, a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, kps, c, ldc, partial); break;
   }
-  if (splitk > 1) {
+  if (partial) {
     const long long total = (long long)M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splitk, M, N, c, ldc);
+    splitk_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, stream>>>(partial, splitk, M, N, c, ldc, 1);
     CL3D_LAUNCHED(1);
   }
   return check_launch("sgemm_tiled_kernel");
+}
+
+// staged floats per k of one problem orientation: (#row tiles) x (#column tiles) x (128 + columns per tile)
+static long long tc_cost(int M, int N) {
+  const int nt = ceil_div(N, 256);
+  const int bn = N >= 256 ? 256 : ((N + 15) & ~15);
+  return (long long)ceil_div(M, kTcBM) * nt * (kTcBM + bn);
+}
+
+static int sgemm_tc(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k, long long sb_n,
+                    int M, int N, int K, float* c, long long ldc, int splitk, float* partial, cudaStream_t stream) {
+  TcGemmArgs g{};
+  // C^T = B^T A^T when that orientation stages fewer operand rows (e.g. a 144 x 80 weight gradient: one
+  // 80(->128) x 144 tile instead of two 128 x 80 tiles)
+  const bool swap = tc_cost(N, M) < tc_cost(M, N);
+  if (!swap) {
+    g.A = a; g.sa_m = sa_m; g.sa_k = sa_k; g.B = b; g.sb_k = sb_k; g.sb_n = sb_n;
+    g.M = M; g.N = N; g.sc_m = ldc; g.sc_n = 1;
+  } else {
+    g.A = b; g.sa_m = sb_n; g.sa_k = sb_k; g.B = a; g.sb_k = sa_k; g.sb_n = sa_m;
+    g.M = N; g.N = M; g.sc_m = 1; g.sc_n = ldc;
+  }
+  g.K = K;
+  int kps = ceil_div(K, splitk);
+  kps = ceil_div(kps, kTcBK) * kTcBK;
+  splitk = ceil_div(K, kps);
+  g.k_per_split = kps;
+  g.C = c;
+  g.partial = splitk > 1 ? partial : nullptr;
+  if (!tc_gemm_supported(g)) return 1;  // caller falls back to the FMA kernel
+  tc_gemm_launch(g, splitk, stream);
+  CL3D_LAUNCHED(1);
+  if (g.partial) {
+    const long long total = (long long)M * N;
+    splitk_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, stream>>>(partial, splitk, g.M, g.N, c, g.sc_m,
+                                                                             g.sc_n);
+    CL3D_LAUNCHED(1);
+  }
+  return check_launch("gemm_tf32x3_kernel");
+}
+
+extern "C" int cl3d_sgemm_algo(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k,
+                               long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk,
+                               void* workspace, size_t workspace_bytes, int algo, cl3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CL3D_REQUIRE(a && b && c && M >= 1 && N >= 1 && K >= 1 && ldc >= N, "cl3d_sgemm: bad arguments");
+  CL3D_REQUIRE(algo == CL3D_GEMM_AUTO || algo == CL3D_GEMM_FFMA || algo == CL3D_GEMM_TC3X, "cl3d_sgemm: bad algo");
+  if (splitk < 1) splitk = 1;
+  if (splitk > K) splitk = K;
+  CL3D_REQUIRE(splitk <= 65535, "cl3d_sgemm: splitk too large");
+  float* partial = nullptr;
+  if (splitk > 1) {
+    if (!workspace || workspace_bytes < cl3d_sgemm_workspace_bytes(M, N, splitk)) {
+      set_error("cl3d_sgemm: split-K workspace too small");
+      return CL3D_ERR_WORKSPACE;
+    }
+    partial = (float*)workspace;
+  }
+  // The tensor core accumulates with truncation (about half an ulp of bias per accumulation step, measured),
+  // so its error grows linearly with the k extent of one accumulator: AUTO keeps it to k ranges <= 512 per
+  // split (error ~1e-6 of the result) and leaves longer un-split reductions to the FMA kernel.
+  if (algo == CL3D_GEMM_AUTO && ceil_div(K, splitk) > 512) algo = CL3D_GEMM_FFMA;
+  if (algo != CL3D_GEMM_FFMA) {
+    const int rc = sgemm_tc(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, c, ldc, splitk, partial, stream);
+    if (rc <= 0) return rc;
+    if (algo == CL3D_GEMM_TC3X) {
+      set_error("cl3d_sgemm: operand extent exceeds the 32-bit offsets of the tensor-core kernel");
+      return CL3D_ERR_UNSUPPORTED;
+    }
+  }
+  return sgemm_ffma(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, c, ldc, splitk, partial, stream);
+}
+
+extern "C" int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k,
+                          long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk, void* workspace,
+                          size_t workspace_bytes, cl3d_stream_t stream_) {
+  return cl3d_sgemm_algo(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, c, ldc, splitk, workspace, workspace_bytes,
+                         CL3D_GEMM_AUTO, stream_);
 }

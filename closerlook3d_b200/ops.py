@@ -197,8 +197,12 @@ def bn_relu_bwd(grad_y, x, stats, gamma, beta, training):
 # --------------------------------------------------------------------------------------------------
 # fp32 GEMM + fused PointWiseMLP
 # --------------------------------------------------------------------------------------------------
-def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1):
-    """out[m][n] = sum_k a[m*sa_m + k*sa_k] * b[k*sb_k + n*sb_n]  (element strides; fp32 FMA)"""
+GEMM_AUTO, GEMM_FFMA, GEMM_TC3X = 0, 1, 2
+
+
+def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1, algo=GEMM_AUTO):
+    """out[m][n] = sum_k a[m*sa_m + k*sa_k] * b[k*sb_k + n*sb_n]  (element strides; fp32 accuracy: 3xTF32 on
+    the tcgen05 tensor cores, or the fp32 FMA kernel -- see cl3d.h)"""
     L = _lib.lib()
     dev = a.device
     ldc = N if ldc is None else ldc
@@ -206,8 +210,8 @@ def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1):
         out = _empty_pm(1, M, ldc, dev).view(M, ldc)
     wsb = L.cl3d_sgemm_workspace_bytes(M, N, splitk)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if splitk > 1 else None
-    check(L.cl3d_sgemm(ptr(a), sa_m, sa_k, ptr(b), sb_k, sb_n, M, N, K, ptr(out), ldc, splitk, ptr(ws), wsb,
-                       stream_ptr()), "cl3d_sgemm")
+    check(L.cl3d_sgemm_algo(ptr(a), sa_m, sa_k, ptr(b), sb_k, sb_n, M, N, K, ptr(out), ldc, splitk, ptr(ws), wsb,
+                            algo, stream_ptr()), "cl3d_sgemm")
     return out
 
 

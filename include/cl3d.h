@@ -199,13 +199,21 @@ int cl3d_bn_relu_bwd(const float* grad_y, const float* x, const float* save_stat
  * fly and the max over K is taken through the monotone BN+ReLU as relu(a*(a>=0?max:min)+b).
  * See DESIGN.md for the kernel list; entry points are declared in the PWMLP section below.
  * ---------------------------------------------------------------------------------------------- */
-/* fp32 FMA GEMM with element strides and optional split-K (gemm.cu):
+/* fp32 GEMM with element strides and optional split-K (gemm.cu, gemm_tc.cuh):
  *   C[m][n] = sum_k A[m*sa_m + k*sa_k] * B[k*sb_k + n*sb_n],  C row stride ldc.
- * splitk > 1 divides k among CTAs (fixed-order reduction); workspace = cl3d_sgemm_workspace_bytes. */
+ * splitk > 1 divides k among CTAs (fixed-order reduction); workspace = cl3d_sgemm_workspace_bytes.
+ * algo: CL3D_GEMM_TC3X = tcgen05 tensor cores with the 3xTF32 operand split (fp32-level accuracy, the default
+ * behind CL3D_GEMM_AUTO), CL3D_GEMM_FFMA = fp32 FMA pipe.  cl3d_sgemm == cl3d_sgemm_algo(..., CL3D_GEMM_AUTO). */
+#define CL3D_GEMM_AUTO 0
+#define CL3D_GEMM_FFMA 1
+#define CL3D_GEMM_TC3X 2
 size_t cl3d_sgemm_workspace_bytes(int M, int N, int splitk);
 int cl3d_sgemm(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k,
                long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk, void* workspace,
                size_t workspace_bytes, cl3d_stream_t stream);
+int cl3d_sgemm_algo(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k,
+                    long long sb_n, int M, int N, int K, float* c, long long ldc, int splitk, void* workspace,
+                    size_t workspace_bytes, int algo, cl3d_stream_t stream);
 
 /* Fused PointWiseMLP (pwmlp.cu).  Cop = cl3d_padded_channels(Cout), Cpa = cl3d_padded_channels(C+3).
  *   cl3d_to_point_major_aug : (B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | xyz/r | 0]

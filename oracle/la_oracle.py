@@ -49,6 +49,13 @@ def make_grouping(ext):
 # against the unmodified reference modules on CPU (tests/test_oracle_cpu.py, tests/golden) keep it False.
 GPU_SCALAR_DIVISION = False
 
+# Same reason, second constant: the reference builds the sin_cos wave lengths with torch.pow ON THE DEVICE of the
+# inputs (local_aggregation_operators.py:72-75).  CPU torch.pow is vectorised differently on different hosts
+# (AVX2 body + scalar tail vs AVX-512), so its last bit is host dependent, and one ulp of a wave length moves
+# sin(100*dp/dim) by up to ~3e-6 coherently over a channel.  GPU parity tests install a function here that
+# evaluates the reference's expression on the GPU (fd -> (fd,) float32 CPU tensor); None = evaluate on the CPU.
+DIM_MAT_FN = None
+
 
 def query_and_group(ext, query_xyz, support_xyz, query_mask, support_mask, features, radius, nsample,
                     normalize_xyz):
@@ -148,7 +155,7 @@ def pospool(ext, st, cfg, cin, cout, radius, nsample, q_xyz, s_xyz, q_mask, s_ma
     elif pe == "sin_cos":                                                     # :70-83
         fd = C // 6
         rng = torch.arange(fd, dtype=torch.float32, device=q_xyz.device)
-        dim_mat = torch.pow(1.0 * 1000, (1.0 / fd) * rng)
+        dim_mat = torch.pow(1.0 * 1000, (1.0 / fd) * rng) if DIM_MAT_FN is None else DIM_MAT_FN(fd).to(rng.device)
         div = torch.div((100 * dp).unsqueeze(-1), dim_mat)                   # (B,3,M,K,fd)
         emb = torch.cat([torch.sin(div), torch.cos(div)], -1)                # (B,3,M,K,2fd)
         emb = emb.permute(0, 1, 4, 2, 3).contiguous().view(B, C, M, nsample)

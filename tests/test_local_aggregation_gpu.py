@@ -61,6 +61,8 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
 
     # ---- forward on both sides (the oracle follows the reference's GPU arithmetic for `/= radius`, see la_oracle)
     la_oracle.GPU_SCALAR_DIVISION = True
+    la_oracle.DIM_MAT_FN = lambda fd: torch.pow(
+        1.0 * 1000, (1.0 / fd) * torch.arange(fd, dtype=torch.float32).to(cuda)).cpu()   # reference :72-75 on its device
     orc = la_oracle.OracleLocalAggregation(oracle_ext, la_type, C, C, r, K, cfg, sd)
     orc.training = train
     f_ref = feats.clone().requires_grad_(True)
@@ -73,6 +75,7 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     # other is inside the output tolerance but flips a whole BN channel's gradient.  Such elements (a handful
     # per million) get zero upstream gradient on BOTH sides, so the comparison is well-posed.
     la_oracle.GPU_SCALAR_DIVISION = False
+    la_oracle.DIM_MAT_FN = None
     flips = (out.detach().cpu() > 0) != (o_ref.detach() > 0)
     assert int(flips.sum()) <= max(2, out.numel() // 100000), f"{int(flips.sum())} ReLU sign flips"
     gout = gout * (~flips)
