@@ -121,7 +121,8 @@ def algo_bytes_per_point(name, C, K, Cout):
         "cl3d_bn_relu_fwd": 8 * C,
         "cl3d_bn_relu_bwd": 12 * C + 8 * C,                    # (grad_y, x) twice, g_pm out
         "cl3d_build_csr": 12 * K + 8,
-        "cl3d_sgemm": 4 * C + 8 * Cop,
+        # three products per step, per call: [f|xyz] row in (or d/dfeat row out) + the 2*Cop-wide A|T row
+        "cl3d_sgemm_algo": 4 * (C + 3) + 8 * Cop,
         "cl3d_pwmlp_fwd_stats": 8 * Cop + 8 * Cout + 2 * Cop + 4 * K + 16,
         "cl3d_pwmlp_fwd_out": 8 * Cout,
         "cl3d_pwmlp_bwd": 16 * Cout + 8 * Cop + 2 * Cop + 4 * K + 16 + 16 * Cop,
@@ -449,13 +450,22 @@ def main():
     roof = None
     if kern:
         top = kern[0]
-        traffic = None
+        # DRAM bytes per launch of the same entry point from the committed `ncu --set full` capture of this workload
+        # (profiles/traffic.json, written by tools/ncu_traffic.py); null when no capture exists for the config
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(f"c{args.config}", {}).get(top["entry"])
+                tj = json.load(f).get(f"c{args.config}", {})
+            ent = tj.get(top["entry"])
+            if ent and res["B_local"] == tj.get("_clouds_per_gpu", res["B_local"]):
+                traffic = ent["dram_bytes_per_step"] / max(1.0, top["calls_per_step"])
+                traffic_src = f"profiles/traffic.json ({tj.get('_report', 'ncu --set full')})"
         roof = {"bound": "hbm", "kernel": top["entry"], "achieved": top["algo_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": (top["algo_gbs"] / peak) if top["algo_gbs"] else None, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "algo_bytes_per_launch": algo_bytes_per_point(top["entry"], C, K, C) * pts_local
+                if algo_bytes_per_point(top["entry"], C, K, C) else None,
                 "peak_source": peak_src, "share_of_step": top["ms_per_step"] / max(1e-9, sum(k["ms_per_step"] for k in kern)),
                 "step_algo_bytes_per_point": 16 * C + 8 * K + 32,
                 "step_frac": (16 * C + 8 * K + 32) * res["value"] / world / 1e9 / peak}

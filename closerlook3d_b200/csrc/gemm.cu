@@ -271,7 +271,8 @@ static int sgemm_tc(const float* a, long long sa_m, long long sa_k, const float*
   TcGemmArgs g{};
   // C^T = B^T A^T when that orientation stages fewer operand rows (e.g. a 144 x 80 weight gradient: one
   // 80(->128) x 144 tile instead of two 128 x 80 tiles)
-  const bool swap = tc_cost(N, M) < tc_cost(M, N);
+  // (only for short M: a long M already fills the machine, and the transposed epilogue is the slower one)
+  const bool swap = M <= 256 && tc_cost(N, M) < tc_cost(M, N);
   if (!swap) {
     g.A = a; g.sa_m = sa_m; g.sa_k = sa_k; g.B = b; g.sb_k = sb_k; g.sb_n = sb_n;
     g.M = M; g.N = N; g.sc_m = ldc; g.sc_n = 1;

@@ -12,8 +12,8 @@
 // One CTA = one 128 x BN output tile (BN = N rounded up to 16, <= 256), 128 threads:
 //   * all threads stage 16-wide k chunks: global (any element strides; float4 along k when possible) ->
 //     registers -> hi/lo split -> shared memory in the canonical K-major no-swizzle UMMA layout
-//       offset(row, k) = (k/4)*LBO + (row/8)*128 + (row%8)*16 + (k%4)*4     [bytes]
-//     i.e. a [k/4][row] array of float4, so the staging stores are conflict-free 16-byte writes;
+//       offset(row, k) = (k/4)*LBO + (row/8)*SBO + (row%8)*16 + (k%4)*4     [bytes]
+//     i.e. a [k/4][row] array of float4 (padded), so the staging stores are conflict-free 16-byte writes;
 //   * thread 0 issues 2 k-steps x 3 tcgen05.mma.kind::tf32 per chunk and commits them to the stage's
 //     mbarrier; a 3-deep ring of stages keeps staging and MMA overlapped (next chunk is prefetched into
 //     registers while the tensor core works);
@@ -28,7 +28,13 @@
 namespace cl3d {
 
 constexpr int kTcBM = 128, kTcBK = 16, kTcStages = 3, kTcProducerWarps = 4, kTcThreads = 32 * (kTcProducerWarps + 1);
-constexpr int kTcPad = 32;  // bytes added to LBO so that 4-threads-per-row staging stores hit distinct banks
+// Shared-memory operand layout (canonical K-major, no swizzle): 8-row x 16-byte core matrices of 128 contiguous
+// bytes, 8-row groups back to back (SBO = 128); LBO = distance between the 16-byte k columns = rows*16 + pad.
+// The pad is chosen per staging mode so that a quarter warp's float4 stores hit 8 distinct 16-byte bank groups:
+// LBO/16 == 2 (mod 8) for mode 1, == 1 (mod 8) for mode 2 (measured: the conflicted transposing map was slower
+// than scalar loads).
+constexpr int kTcSbo = 128;
+__host__ __device__ inline int tc_row_off(int r) { return r * 16; }
 
 struct TcGemmArgs {
   const float* A; long long sa_m, sa_k;
@@ -115,13 +121,13 @@ __device__ __forceinline__ float4 tc_load4(const float* __restrict__ p, int sk, 
   return v;
 }
 
-__host__ __device__ inline int tc_lbo(int rows) { return rows * 16 + kTcPad; }
+__host__ __device__ inline int tc_lbo(int rows, int mode = 1) { return rows * 16 + (mode == 2 ? 16 : 32); }
 __host__ __device__ inline size_t tc_stage_bytes(int bn) { return 2 * 4 * (size_t)tc_lbo(kTcBM) + 2 * 4 * (size_t)tc_lbo(bn); }
 __host__ inline size_t tc_smem_bytes(int bn) { return kTcStages * tc_stage_bytes(bn) + 16 * kTcStages + 16; }
 
-// NB = float4 of the B chunk per thread (ceil(BN*4/128)); AV / BV: float4 loads along k are legal.
-// Warps 0..3 stage operands and run the epilogue; warp 4 owns tensor memory and issues the MMAs.
-template <int NB, bool AV, bool BV>
+// NB = float4 of the B chunk per thread (ceil(BN*4/128)); AV / BV: how the operand is read (staging modes
+// below: 1 = float4 along k, 2 = float4 along the rows + register transpose, 0 = scalar).  Warps 0..3 stage operands and run the epilogue; warp 4 owns tensor memory and issues the MMAs.
+template <int NB, int AV, int BV>
 __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_kernel(const TcGemmArgs g) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_kernel(const TcGemmArg
   const int bn = min(256, ((g.N - n0) + 15) & ~15);  // columns of this tile (multiple of 16)
   const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
   const int nchunks = (kend - kbeg + kTcBK - 1) / kTcBK;
-  const int lbo_a = tc_lbo(kTcBM), lbo_b = tc_lbo(bn);
+  const int lbo_a = tc_lbo(kTcBM, AV), lbo_b = tc_lbo(bn, BV);
   const uint32_t stage_bytes = (uint32_t)tc_stage_bytes(bn);
   uint64_t* full = reinterpret_cast<uint64_t*>(tc_smem + kTcStages * stage_bytes);  // producers -> MMA warp
   uint64_t* empty = full + kTcStages;                                                // MMA completion -> producers
@@ -155,48 +161,89 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_kernel(const TcGemmArg
 
   if (warp < kTcProducerWarps) {
     // ---------------------------------------------------------------------------------- producers
-    // staging maps (fixed per thread): k-fast operands use 4 threads per row (64 contiguous bytes of global
-    // memory), the others one row per thread (consecutive threads -> consecutive unit-stride rows)
+    // staging maps (fixed per thread), one float4 = 4 consecutive k of one row once it is in shared memory:
+    //   mode 1 (k is the unit stride): 4 threads per row, each loads its float4 directly (64 contiguous bytes/row)
+    //   mode 2 (row is the unit stride): a thread loads a 4 (k) x 4 (rows) block as four float4 along the rows
+    //           (a warp reads 4 k-rows x 128 contiguous bytes per instruction) and transposes it in registers
+    //   mode 0 (anything else): one row per thread, four scalar loads
     const int ska = (int)g.sa_k, skb = (int)g.sb_k;
     const int nb4 = bn * 4;
+    constexpr int RB = BV == 2 ? (NB == 3 ? 4 : 8) : NB;  // float4 registers of the B chunk per thread
     uint32_t ga[4], sa[4], gb[NB], sb[NB];  // element offset in global memory, byte offset in the stage
+    if constexpr (AV == 2) {
+      const int mg = tid >> 2, c = tid & 3;
+      ga[0] = (uint32_t)((long long)min(m0 + 4 * mg, g.M - 4) + (long long)(4 * c) * g.sa_k);
+      sa[0] = (uint32_t)(c * lbo_a + tc_row_off(4 * mg));
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = tid + 128 * j;
-      const int r = AV ? (e >> 2) : (e & (kTcBM - 1)), c = AV ? (e & 3) : (e >> 7);
-      ga[j] = (uint32_t)((long long)min(m0 + r, g.M - 1) * g.sa_m + (long long)(4 * c) * g.sa_k);
-      sa[j] = (uint32_t)(c * lbo_a + r * 16);
+      for (int j = 0; j < 4; ++j) {
+        const int e = tid + 128 * j;
+        const int r = AV ? (e >> 2) : (e & (kTcBM - 1)), c = AV ? (e & 3) : (e >> 7);
+        ga[j] = (uint32_t)((long long)min(m0 + r, g.M - 1) * g.sa_m + (long long)(4 * c) * g.sa_k);
+        sa[j] = (uint32_t)(c * lbo_a + tc_row_off(r));
+      }
     }
+    int cb2[2] = {0, 0};
+    if constexpr (BV == 2) {
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int e = min(tid + 128 * j, nb4 - 1);
-      const int r = BV ? (e >> 2) : (e % bn), c = BV ? (e & 3) : (e / bn);
-      gb[j] = (uint32_t)((long long)min(n0 + r, g.N - 1) * g.sb_n + (long long)(4 * c) * g.sb_k);
-      sb[j] = (uint32_t)(8 * lbo_a + c * lbo_b + r * 16);
+      for (int j = 0; j < RB / 4; ++j) {
+        const int e = min(tid + 128 * j, bn - 1);
+        const int mg = e >> 2, c = e & 3;
+        cb2[j] = c;
+        gb[j] = (uint32_t)((long long)min(n0 + 4 * mg, g.N - 4) + (long long)(4 * c) * g.sb_k);
+        sb[j] = (uint32_t)(8 * lbo_a + c * lbo_b + tc_row_off(4 * mg));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int e = min(tid + 128 * j, nb4 - 1);
+        const int r = BV ? (e >> 2) : (e % bn), c = BV ? (e & 3) : (e / bn);
+        gb[j] = (uint32_t)((long long)min(n0 + r, g.N - 1) * g.sb_n + (long long)(4 * c) * g.sb_k);
+        sb[j] = (uint32_t)(8 * lbo_a + c * lbo_b + tc_row_off(r));
+      }
     }
-    const int ca = AV ? (tid & 3) : 0, cb = BV ? (tid & 3) : 0;  // k column (of 4) -- only used for the k tail
+    const int ca = tid & 3, cb = tid & 3;  // k column (of 4), k tail only
 
-    float4 ra0[4], rb0[NB], ra1[4], rb1[NB];  // two chunks in flight per thread
-    auto load_chunk = [&](int k0, float4 (&ra)[4], float4 (&rb)[NB]) {
+    float4 ra0[4], rb0[RB], ra1[4], rb1[RB];  // two chunks in flight per thread
+    auto load_chunk = [&](int k0, float4 (&ra)[4], float4 (&rb)[RB]) {
       const float* Ak = g.A + (long long)k0 * g.sa_k;
       const float* Bk = g.B + (long long)k0 * g.sb_k;
-      if (k0 + kTcBK <= kend) {
+      const bool full_chunk = k0 + kTcBK <= kend;
+      if constexpr (AV == 2) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ra[j] = tc_load4<AV, true>(Ak + ga[j], ska, 0, 0);
+        for (int kk = 0; kk < 4; ++kk) {
+          ra[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (full_chunk || k0 + 4 * ca + kk < kend) ra[kk] = __ldg(reinterpret_cast<const float4*>(Ak + ga[0] + kk * ska));
+        }
+      } else if (full_chunk) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j)
-          if (tid + 128 * j < nb4) rb[j] = tc_load4<BV, true>(Bk + gb[j], skb, 0, 0);
+        for (int j = 0; j < 4; ++j) ra[j] = tc_load4<AV == 1, true>(Ak + ga[j], ska, 0, 0);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ra[j] = tc_load4<AV, false>(Ak + ga[j], ska, k0 + 4 * (AV ? ca : j), kend);
+        for (int j = 0; j < 4; ++j) ra[j] = tc_load4<AV == 1, false>(Ak + ga[j], ska, k0 + 4 * (AV ? ca : j), kend);
+      }
+      if constexpr (BV == 2) {
+#pragma unroll
+        for (int j = 0; j < RB / 4; ++j)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            rb[4 * j + kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid + 128 * j < bn && (full_chunk || k0 + 4 * cb2[j] + kk < kend))
+              rb[4 * j + kk] = __ldg(reinterpret_cast<const float4*>(Bk + gb[j] + kk * skb));
+          }
+      } else if (full_chunk) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (tid + 128 * j < nb4) rb[j] = tc_load4<BV == 1, true>(Bk + gb[j], skb, 0, 0);
+      } else {
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           const int e = tid + 128 * j;
-          if (e < nb4) rb[j] = tc_load4<BV, false>(Bk + gb[j], skb, k0 + 4 * (BV ? cb : e / bn), kend);
+          if (e < nb4) rb[j] = tc_load4<BV == 1, false>(Bk + gb[j], skb, k0 + 4 * (BV ? cb : e / bn), kend);
         }
       }
     };
-    auto step = [&](int i, float4 (&ra)[4], float4 (&rb)[NB]) {
+    auto step = [&](int i, float4 (&ra)[4], float4 (&rb)[RB]) {
       const int s = i % kTcStages;
       unsigned char* st = tc_smem + (size_t)s * stage_bytes;
       if (i < 8) TC_STAMP(16 + 6 * i);
@@ -204,11 +251,30 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_kernel(const TcGemmArg
       if (i < 8) TC_STAMP(17 + 6 * i);
       unsigned char* lo_a = st + 4 * lbo_a;
       unsigned char* lo_b = st + 4 * lbo_b;
+      if constexpr (AV == 2) {
+        tc_split_store(st, lo_a, sa[0], make_float4(ra[0].x, ra[1].x, ra[2].x, ra[3].x));
+        tc_split_store(st, lo_a, sa[0] + 16, make_float4(ra[0].y, ra[1].y, ra[2].y, ra[3].y));
+        tc_split_store(st, lo_a, sa[0] + 32, make_float4(ra[0].z, ra[1].z, ra[2].z, ra[3].z));
+        tc_split_store(st, lo_a, sa[0] + 48, make_float4(ra[0].w, ra[1].w, ra[2].w, ra[3].w));
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) tc_split_store(st, lo_a, sa[j], ra[j]);
+        for (int j = 0; j < 4; ++j) tc_split_store(st, lo_a, sa[j], ra[j]);
+      }
+      if constexpr (BV == 2) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        if (tid + 128 * j < nb4) tc_split_store(st, lo_b, sb[j], rb[j]);
+        for (int j = 0; j < RB / 4; ++j)
+          if (tid + 128 * j < bn) {
+            const float4 r0 = rb[4 * j], r1 = rb[4 * j + 1], r2 = rb[4 * j + 2], r3 = rb[4 * j + 3];
+            tc_split_store(st, lo_b, sb[j], make_float4(r0.x, r1.x, r2.x, r3.x));
+            tc_split_store(st, lo_b, sb[j] + 16, make_float4(r0.y, r1.y, r2.y, r3.y));
+            tc_split_store(st, lo_b, sb[j] + 32, make_float4(r0.z, r1.z, r2.z, r3.z));
+            tc_split_store(st, lo_b, sb[j] + 48, make_float4(r0.w, r1.w, r2.w, r3.w));
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (tid + 128 * j < nb4) tc_split_store(st, lo_b, sb[j], rb[j]);
+      }
       if (i < 8) TC_STAMP(18 + 6 * i);
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&full[s]);
@@ -335,7 +401,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_kernel(const TcGemmArg
     const uint32_t tmem = *tmem_slot;
     if (lane == 0) {
       const uint32_t idesc = tc_idesc_tf32(bn);
-      const uint64_t dhi_a = tc_smem_desc_hi((uint32_t)lbo_a, 128u), dhi_b = tc_smem_desc_hi((uint32_t)lbo_b, 128u);
+      const uint64_t dhi_a = tc_smem_desc_hi((uint32_t)lbo_a, kTcSbo), dhi_b = tc_smem_desc_hi((uint32_t)lbo_b, kTcSbo);
       for (int i = 0; i < nchunks; ++i) {
         const int s = i % kTcStages;
         mbar_wait(&full[s], (uint32_t)((i / kTcStages) & 1));  // all 128 producers have staged chunk i
@@ -369,28 +435,39 @@ inline bool tc_gemm_supported(const TcGemmArgs& g) {
          ext(g.N, g.sb_n, g.K, g.sb_k) < lim && g.sa_k < (1 << 28) && g.sb_k < (1 << 28);
 }
 
-template <int NB>
-inline void tc_gemm_launch_nb(const TcGemmArgs& g, bool av, bool bv, dim3 grid, size_t smem, cudaStream_t stream) {
+template <int NB, int AV, int BV>
+inline void tc_gemm_launch_k(const TcGemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    const int mx = (int)tc_smem_bytes(NB == 3 ? 96 : NB == 5 ? 160 : 256);
-    cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, AV, BV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)tc_smem_bytes(NB == 3 ? 96 : NB == 5 ? 160 : 256));
     attr_set = true;
   }
-  if (av && bv) gemm_tf32x3_kernel<NB, true, true><<<grid, kTcThreads, smem, stream>>>(g);
-  else if (av) gemm_tf32x3_kernel<NB, true, false><<<grid, kTcThreads, smem, stream>>>(g);
-  else if (bv) gemm_tf32x3_kernel<NB, false, true><<<grid, kTcThreads, smem, stream>>>(g);
-  else gemm_tf32x3_kernel<NB, false, false><<<grid, kTcThreads, smem, stream>>>(g);
+  gemm_tf32x3_kernel<NB, AV, BV><<<grid, kTcThreads, smem, stream>>>(g);
+}
+
+template <int NB, int AV>
+inline void tc_gemm_launch_b(const TcGemmArgs& g, int bv, dim3 grid, size_t smem, cudaStream_t stream) {
+  if (bv == 1) tc_gemm_launch_k<NB, AV, 1>(g, grid, smem, stream);
+  else if (bv == 2) tc_gemm_launch_k<NB, AV, 2>(g, grid, smem, stream);
+  else tc_gemm_launch_k<NB, AV, 0>(g, grid, smem, stream);
+}
+
+template <int NB>
+inline void tc_gemm_launch_nb(const TcGemmArgs& g, int av, int bv, dim3 grid, size_t smem, cudaStream_t stream) {
+  if (av == 1) tc_gemm_launch_b<NB, 1>(g, bv, grid, smem, stream);
+  else if (av == 2) tc_gemm_launch_b<NB, 2>(g, bv, grid, smem, stream);
+  else tc_gemm_launch_b<NB, 0>(g, bv, grid, smem, stream);
 }
 
 // Launch.  k_per_split must be a multiple of kTcBK when splits > 1.
 inline void tc_gemm_launch(const TcGemmArgs& g, int splits, cudaStream_t stream) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool av = g.sa_k == 1 && al16(g.A) && g.sa_m % 4 == 0 && g.K % 4 == 0 && g.k_per_split % 4 == 0;
-  const bool bv = g.sb_k == 1 && al16(g.B) && g.sb_n % 4 == 0 && g.K % 4 == 0 && g.k_per_split % 4 == 0;
+  const bool kal = g.K % 4 == 0 && g.k_per_split % 4 == 0;
+  const int av = (g.sa_k == 1 && al16(g.A) && g.sa_m % 4 == 0 && kal) ? 1
+                 : (g.sa_m == 1 && al16(g.A) && g.sa_k % 4 == 0 && g.M % 4 == 0) ? 2 : 0;
+  const int bv = (g.sb_k == 1 && al16(g.B) && g.sb_n % 4 == 0 && kal) ? 1
+                 : (g.sb_n == 1 && al16(g.B) && g.sb_k % 4 == 0 && g.N % 4 == 0) ? 2 : 0;
   const int bn = g.N >= 256 ? 256 : ((g.N + 15) & ~15);
   const size_t smem = tc_smem_bytes(bn);
   dim3 grid((g.N + 255) / 256, (g.M + kTcBM - 1) / kTcBM, splits);

@@ -61,7 +61,7 @@ class _FusedPointWiseMLP(Function):
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             # d/dwcat (2Cop x Cpa) = grad_AB^T (2Cop x P) @ fa (P x Cpa): long reduction -> split-K
-            splitk = max(1, min(1024, P // 256))   # <= 256 points per partial sum (see cl3d_sgemm_algo)
+            splitk = max(1, min(1024, P // 128))   # ~128 points per partial sum (see cl3d_sgemm_algo)
             gwcat = ops.sgemm(grad_ab, 1, 2 * Cop, fa_pm, Cpa, 1, 2 * Cop, Cpa, P, splitk=splitk)
             gW = ops.pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout)
         # d/dfeat (point-major) = grad_AB (P x 2Cop) @ wcat[:, :Cp] (2Cop x Cp; columns >= C are unused)

@@ -63,3 +63,17 @@ def test_sgemm_tc_aligned_weight_gradient(cuda):
     for algo in (1, 2):
         out = ops.sgemm(ga, 1, M, f, N, 1, M, N, P, splitk=128, algo=algo)
         assert float((out[:, :N] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), algo
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("M,N,K", [(512, 144, 150), (132, 72, 16), (4096, 80, 37)])
+def test_sgemm_row_contiguous_operands(cuda, M, N, K, algo):
+    """both operands stored k-major-outer (rows are the unit stride, 16-byte aligned): the tensor-core kernel
+    stages them with float4 loads along the rows and a register transpose; K = 150 / 37 exercise the k tail"""
+    from closerlook3d_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    at = torch.randn(K, M, generator=g).to(cuda)      # A[m][k] = at[k][m]
+    b = torch.randn(K, N, generator=g).to(cuda)       # B[k][n]
+    out = ops.sgemm(at, 1, M, b, N, 1, M, N, K, algo=algo)
+    ref = (at.double().t() @ b.double()).float()
+    assert float((out[:, :N] - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
