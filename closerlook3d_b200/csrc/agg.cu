@@ -119,6 +119,34 @@ __device__ __forceinline__ float pg_influence(float dx, float dy, float dz, cons
   return h > 0.f ? h : 0.f;
 }
 
+// PseudoGrid staging with compaction: a slot whose influences are all zero (the neighbour is farther than
+// `extent` from every kernel point -- about 40 % of the slots of BASELINE c3, 2 of 15 influences non-zero on
+// average) contributes exact zeros to every sum, so it is not staged at all: no row gather, no FMAs.  The
+// surviving slots keep their order, so the result is bit-identical to the dense evaluation.
+// All 32 lanes call this; returns the number of staged slots.
+__device__ __forceinline__ int pg_stage_slots(float4* __restrict__ s_dp, float* __restrict__ s_h, int* __restrict__ s_m,
+                                              bool valid, float dx, float dy, float dz, unsigned row_off,
+                                              const float* __restrict__ kpts, int nkp, int influence, float inv_extent) {
+  float h[kMaxKP];
+  unsigned nz = 0;  // bit kp set <=> influence of kernel point kp is non-zero
+#pragma unroll
+  for (int kp = 0; kp < kMaxKP; ++kp) {
+    h[kp] = (valid && kp < nkp) ? pg_influence(dx, dy, dz, kpts + kp * 3, influence, inv_extent) : 0.f;
+    nz |= h[kp] > 0.f ? (1u << kp) : 0u;
+  }
+  const bool any = nz != 0;
+  const unsigned m = __ballot_sync(0xffffffffu, any);
+  if (any) {
+    const int pos = __popc(m & ((1u << lane_id()) - 1u));
+    s_dp[pos] = make_float4(dx, dy, dz, __uint_as_float(row_off));
+    s_m[pos] = (int)nz;
+    float4* h4 = reinterpret_cast<float4*>(s_h + (size_t)pos * kMaxKP);
+#pragma unroll
+    for (int k4 = 0; k4 < kMaxKP / 4; ++k4) h4[k4] = make_float4(h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
+  }
+  return __popc(m);
+}
+
 template <int FAM>
 constexpr int rows_in_flight() {  // independent row loads per lane before they are consumed
   return (FAM == CL3D_FAM_PSEUDOGRID || FAM == CL3D_FAM_POSPOOL_SINCOS) ? 2 : 4;
@@ -130,7 +158,7 @@ constexpr int num_acc() {
 
 // shared-memory carve-up (per CTA): per-warp slot arrays (dp + row index, influences / scales) + output tile
 struct SmemLayout {
-  size_t dp_off, h_off, out_off, red_off, total;
+  size_t dp_off, h_off, m_off, out_off, red_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int chunkC, int red_floats) {
   SmemLayout L;
@@ -139,6 +167,8 @@ __host__ __device__ inline SmemLayout smem_layout(int chunkC, int red_floats) {
   o += (size_t)kAggWarps * kSlots * sizeof(float4);
   L.h_off = o;
   o += (size_t)kAggWarps * kSlots * kMaxKP * sizeof(float);
+  L.m_off = o;
+  o += (size_t)kAggWarps * kSlots * sizeof(int);  // PseudoGrid: non-zero-influence bit mask per slot
   L.out_off = o;
   o += (size_t)chunkC * (kTile + 1) * sizeof(float);
   o = align_up(o, 16);
@@ -153,23 +183,23 @@ __host__ __device__ inline SmemLayout smem_layout(int chunkC, int red_floats) {
 // registers); PseudoGrid backward accumulates T[k'][c] = sum_e g[c] h[k',e] (needed for d/dWk anyway).
 template <int FAM, int CI, bool BWD, int NACC, int NWK>
 __device__ __forceinline__ void apply_slot(const float (&v)[CI], const float4& dp, const float* __restrict__ hk,
+                                           unsigned hmask, const float* __restrict__ s_wk_lane,
                                            const LaneParams<FAM, CI>& lp, const float (&wk)[NWK][CI],
                                            float (&acc)[NACC][CI]) {
   if constexpr (FAM == CL3D_FAM_PSEUDOGRID && !BWD) {
-    const float4* h4 = reinterpret_cast<const float4*>(hk);  // 16 influences of this slot (0 beyond nkp)
+    // w[c] = sum over the NON-ZERO influences only (about 3 of 15, warp-uniform bit mask), ascending k' -- the
+    // skipped terms are exact zeros; kernel weights come from shared memory (dynamic k').
     float w[CI];
 #pragma unroll
     for (int i = 0; i < CI; ++i) w[i] = 0.f;
+    unsigned mm = hmask;
+    while (mm) {
+      const int kp = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const float h = hk[kp];
+      const float* wrow = s_wk_lane + kp * (32 * CI);
 #pragma unroll
-    for (int k4 = 0; k4 < kMaxKP / 4; ++k4) {
-      const float4 h = h4[k4];
-#pragma unroll
-      for (int i = 0; i < CI; ++i) {
-        w[i] = fmaf(h.x, wk[k4 * 4 + 0][i], w[i]);
-        w[i] = fmaf(h.y, wk[k4 * 4 + 1][i], w[i]);
-        w[i] = fmaf(h.z, wk[k4 * 4 + 2][i], w[i]);
-        w[i] = fmaf(h.w, wk[k4 * 4 + 3][i], w[i]);
-      }
+      for (int i = 0; i < CI; ++i) w[i] = fmaf(h, wrow[32 * i], w[i]);
     }
 #pragma unroll
     for (int i = 0; i < CI; ++i) acc[0][i] = fmaf(v[i], w[i], acc[0][i]);
@@ -213,9 +243,11 @@ __device__ __forceinline__ void apply_slot(const float (&v)[CI], const float4& d
 // Rows are loaded U at a time straight into registers (U*CI independent loads in flight per lane).
 template <int FAM, int CI, bool BWD, int NACC, int NWK>
 __device__ __forceinline__ void consume_slots(const float* __restrict__ lbase,
-                                              const float4* __restrict__ s_dp, const float* __restrict__ s_h, int n,
+                                              const float4* __restrict__ s_dp, const float* __restrict__ s_h,
+                                              const int* __restrict__ s_m, const float* __restrict__ s_wk_lane, int n,
                                               const LaneParams<FAM, CI>& lp, const float (&wk)[NWK][CI],
                                               float (&acc)[NACC][CI]) {
+  constexpr bool MASKED = FAM == CL3D_FAM_PSEUDOGRID && !BWD;
   constexpr int U = rows_in_flight<FAM>();
   constexpr int HS = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;  // floats of s_h per slot
   // software pipeline: group g+1 is loaded into the other register set while group g is consumed
@@ -230,7 +262,9 @@ __device__ __forceinline__ void consume_slots(const float* __restrict__ lbase,
   };
   auto apply_group = [&](int s0, const float4 (&dp)[U], const float (&v)[U][CI]) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) apply_slot<FAM, CI, BWD, NACC, NWK>(v[u], dp[u], s_h + (size_t)(s0 + u) * HS, lp, wk, acc);
+    for (int u = 0; u < U; ++u)
+      apply_slot<FAM, CI, BWD, NACC, NWK>(v[u], dp[u], s_h + (size_t)(s0 + u) * HS, MASKED ? (unsigned)s_m[s0 + u] : 0u,
+                                          s_wk_lane, lp, wk, acc);
   };
   const int ng = n / U;
   if constexpr (FAM == CL3D_FAM_PSEUDOGRID && BWD) {
@@ -261,7 +295,7 @@ __device__ __forceinline__ void consume_slots(const float* __restrict__ lbase,
     float v[CI];
 #pragma unroll
     for (int i = 0; i < CI; ++i) v[i] = __ldg(row + 32 * i);
-    apply_slot<FAM, CI, BWD, NACC, NWK>(v, dp, s_h + (size_t)s * HS, lp, wk, acc);
+    apply_slot<FAM, CI, BWD, NACC, NWK>(v, dp, s_h + (size_t)s * HS, MASKED ? (unsigned)s_m[s] : 0u, s_wk_lane, lp, wk, acc);
   }
 }
 
@@ -277,7 +311,9 @@ __global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2
   const SmemLayout L = smem_layout(32 * CI, 0);
   float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
   float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * kSlots * kMaxKP;
+  int* s_m = reinterpret_cast<int*>(smem + L.m_off) + (size_t)warp * kSlots;
   float* s_out = reinterpret_cast<float*>(smem + L.out_off);
+  float* s_wk = reinterpret_cast<float*>(smem + L.total);  // PseudoGrid: kernel weights [kMaxKP][32*CI]
 
   const int tiles_per_cloud = (a.M + kTile - 1) / kTile;
   const int b = blockIdx.x / tiles_per_cloud;
@@ -286,15 +322,15 @@ __global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2
   LaneParams<FAM, CI> lp;
   load_lane_params<FAM, CI>(lp, a, c0, lane);
   constexpr int NACC = num_acc<FAM, false>();
-  constexpr int NWK = FAM == CL3D_FAM_PSEUDOGRID ? kMaxKP : 1;
-  float wk[NWK][CI];
-#pragma unroll
-  for (int kp = 0; kp < NWK; ++kp)
-#pragma unroll
-    for (int i = 0; i < CI; ++i) {
-      const int c = c0 + lane + 32 * i;
-      wk[kp][i] = (FAM == CL3D_FAM_PSEUDOGRID && kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
+  constexpr int NWK = 1;
+  const float wk[NWK][CI] = {};
+  if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
+    for (int e = threadIdx.x; e < kMaxKP * 32 * CI; e += blockDim.x) {
+      const int kp = e / (32 * CI), c = c0 + e % (32 * CI);
+      s_wk[e] = (kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
     }
+    __syncthreads();
+  }
   const float* feat = a.feat_pm + (size_t)b * a.N * a.Cp + c0 + lane;  // per-lane base pointer
   const float* sxyz = a.support_xyz + (size_t)b * a.N * 3;
 
@@ -313,26 +349,30 @@ __global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2
 #pragma unroll
         for (int i = 0; i < CI; ++i) acc[s][i] = 0.f;
       for (int k0 = 0; k0 < nrows; k0 += kSlots) {
-        const int rows = min(kSlots, nrows - k0);
+        int rows = min(kSlots, nrows - k0);
         // ---- stage: indices, relative positions (pt_utils.py:127-129), PseudoGrid influences
-        if (lane < rows) {
-          const int j = a.idx[gq * a.K + k0 + lane];
-          float dx = __fsub_rn(sxyz[j * 3 + 0], qx), dy = __fsub_rn(sxyz[j * 3 + 1], qy),
-                dz = __fsub_rn(sxyz[j * 3 + 2], qz);
-          if (a.normalize) {  // torch's CUDA `tensor /= python_scalar` multiplies by the fp32 reciprocal
-            dx = __fmul_rn(dx, a.inv_radius);
-            dy = __fmul_rn(dy, a.inv_radius);
-            dz = __fmul_rn(dz, a.inv_radius);
+        {
+          const bool valid = lane < rows;
+          float dx = 0.f, dy = 0.f, dz = 0.f;
+          unsigned roff = 0;
+          if (valid) {
+            const int j = a.idx[gq * a.K + k0 + lane];
+            dx = __fsub_rn(sxyz[j * 3 + 0], qx), dy = __fsub_rn(sxyz[j * 3 + 1], qy), dz = __fsub_rn(sxyz[j * 3 + 2], qz);
+            if (a.normalize) {  // torch's CUDA `tensor /= python_scalar` multiplies by the fp32 reciprocal
+              dx = __fmul_rn(dx, a.inv_radius);
+              dy = __fmul_rn(dy, a.inv_radius);
+              dz = __fmul_rn(dz, a.inv_radius);
+            }
+            roff = (unsigned)j * (unsigned)a.Cp;
           }
-          s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)j * (unsigned)a.Cp));
           if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
-            for (int kp = 0; kp < a.nkp; ++kp)
-              s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.inv_extent);
-            for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[lane * kMaxKP + kp] = 0.f;
+            rows = pg_stage_slots(s_dp, s_h, s_m, valid, dx, dy, dz, roff, a.p0, a.nkp, a.influence, a.inv_extent);
+          } else {
+            if (valid) s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float(roff));
           }
         }
         __syncwarp();
-        consume_slots<FAM, CI, false, NACC, NWK>(feat, s_dp, s_h, rows, lp, wk, acc);
+        consume_slots<FAM, CI, false, NACC, NWK>(feat, s_dp, s_h, s_m, s_wk + lane, rows, lp, wk, acc);
         __syncwarp();  // slots are rewritten by the next round / query
       }
       if constexpr (FAM == CL3D_FAM_PSEUDOGRID) {
@@ -397,6 +437,7 @@ __global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2
   const SmemLayout L = smem_layout(32 * CI, ppc * 32 * CI);
   float4* s_dp = reinterpret_cast<float4*>(smem + L.dp_off) + (size_t)warp * kSlots;
   float* s_h = reinterpret_cast<float*>(smem + L.h_off) + (size_t)warp * kSlots * kMaxKP;
+  int* s_m = reinterpret_cast<int*>(smem + L.m_off) + (size_t)warp * kSlots;
   float* s_out = reinterpret_cast<float*>(smem + L.out_off);
   float* s_red = reinterpret_cast<float*>(smem + L.red_off);
   float* s_wk = reinterpret_cast<float*>(smem + L.total);                 // [kMaxKP][32*CI]      (PG only)
@@ -449,27 +490,31 @@ __global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2
           for (int i = 0; i < CI; ++i) acc[s][i] = 0.f;
 
         for (int eb = e0; eb < e1; eb += kSlots) {
-          const int rows = min(kSlots, e1 - eb);
-          if (lane < rows) {
-            const int q = ent[eb + lane] / a.K;
-            float dx = __fsub_rn(px, qxyz[q * 3 + 0]), dy = __fsub_rn(py, qxyz[q * 3 + 1]),
-                  dz = __fsub_rn(pz, qxyz[q * 3 + 2]);
-            if (a.normalize) {
-              dx = __fmul_rn(dx, a.inv_radius);
-              dy = __fmul_rn(dy, a.inv_radius);
-              dz = __fmul_rn(dz, a.inv_radius);
+          int rows = min(kSlots, e1 - eb);
+          {
+            const bool valid = lane < rows;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            unsigned roff = 0;
+            int q = 0;
+            if (valid) {
+              q = ent[eb + lane] / a.K;
+              dx = __fsub_rn(px, qxyz[q * 3 + 0]), dy = __fsub_rn(py, qxyz[q * 3 + 1]), dz = __fsub_rn(pz, qxyz[q * 3 + 2]);
+              if (a.normalize) {
+                dx = __fmul_rn(dx, a.inv_radius);
+                dy = __fmul_rn(dy, a.inv_radius);
+                dz = __fmul_rn(dz, a.inv_radius);
+              }
+              roff = (unsigned)q * (unsigned)a.Cp;
             }
-            s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float((unsigned)q * (unsigned)a.Cp));
             if constexpr (PG) {
-              for (int kp = 0; kp < a.nkp; ++kp)
-                s_h[lane * kMaxKP + kp] = pg_influence(dx, dy, dz, a.p0 + kp * 3, a.influence, a.inv_extent);
-              for (int kp = a.nkp; kp < kMaxKP; ++kp) s_h[lane * kMaxKP + kp] = 0.f;
-            } else {
+              rows = pg_stage_slots(s_dp, s_h, s_m, valid, dx, dy, dz, roff, a.p0, a.nkp, a.influence, a.inv_extent);
+            } else if (valid) {
+              s_dp[lane] = make_float4(dx, dy, dz, __uint_as_float(roff));
               s_h[lane * HS] = a.reduction == CL3D_REDUCE_AVG ? __fdiv_rn(1.f, (float)ncnt[q]) : 1.f;
             }
           }
           __syncwarp();
-          consume_slots<FAM, CI, true, NACC, 1>(gpm, s_dp, s_h, rows, lp, wk_dummy, acc);
+          consume_slots<FAM, CI, true, NACC, 1>(gpm, s_dp, s_h, s_m, nullptr, rows, lp, wk_dummy, acc);
           __syncwarp();
         }
         // ---- epilogue: gradient w.r.t. this support point's features, parameter gradients
@@ -814,10 +859,11 @@ template <int FAM, int CI>
 static int launch_fwd(const AggArgs& a, cudaStream_t stream) {
   const int nchunks = ceil_div(a.Cp, 32 * CI);
   const SmemLayout L = smem_layout(32 * CI, 0);
-  if (L.total > 48 * 1024)
-    cudaFuncSetAttribute(agg_fwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  const size_t smem = L.total + (FAM == CL3D_FAM_PSEUDOGRID ? (size_t)kMaxKP * 32 * CI * sizeof(float) : 0);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(agg_fwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(a.ntiles, nchunks);
-  agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
+  agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, smem, stream>>>(a);
   CL3D_LAUNCHED(1);
   return check_launch("agg_fwd_kernel");
 }
