@@ -32,6 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per stream (copy / search / step)
 import torch  # noqa: E402
 
 
@@ -140,6 +141,47 @@ def build_module(spec, device):
     r = synth.ball_radius(spec["N"], spec["K"])
     mod = LocalAggregation(spec["C"], spec["C"], r, spec["K"], spec["cfg"])
     return mod.to(device), r
+
+
+class numa_local:
+    """Bind the CALLING THREAD to the CPUs NVML reports as local to the GPU for the end-to-end leg: the pinned host
+    buffers are allocated on that NUMA node (cudaHostAlloc places pages on the caller's node; the H2D copies are DMA
+    from there) and the launching thread does not pay cross-socket latency per CUDA call; then restore the
+    thread's affinity.  The intra-op thread pools are created before the first use (full mask), so the CPU legs
+    of this script are not affected.  Any failure leaves the affinity untouched."""
+
+    def __init__(self, device):
+        self.device, self.saved, self.cpus = device, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            torch.ones(1 << 22).sum().item()          # create torch's CPU thread pool with the unrestricted mask
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.device.index or 0)
+            n = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            saved = os.sched_getaffinity(0)
+            cpus &= saved
+            if cpus and cpus != saved:
+                os.sched_setaffinity(0, cpus)
+                self.saved, self.cpus = saved, cpus
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
 
 
 def make_ring(spec, B_local, rank, device, min_bytes, pinned=False):
@@ -253,52 +295,68 @@ def run_ours(args, spec, rank, world, device):
     #      inside the timed region).  With graphs: closerlook3d_b200.graphed.PipelinedTrainer overlaps the copy of
     #      batch i+1 with the replay of batch i (double-buffered static inputs) and reads results one step late.
     e2e = None
-    hring = make_ring(spec, B_local, rank, device, 0.0, pinned=True)
-    h2d = sum(v.numel() * v.element_size() for v in hring[0].values())
-    nst = max(5, min(args.steps, 30))
+    with numa_local(device) as nl:
+        hring = make_ring(spec, B_local, rank, device, 0.0, pinned=True)
+        h2d = sum(v.numel() * v.element_size() for v in hring[0].values())
+        nst = max(args.steps, 100)   # ~30 ms of wall clock at c2: short windows are dominated by host jitter
+        # the host link on its own: one batch, pinned -> device, 10 back-to-back copies (the e2e rate cannot exceed
+        # points_per_batch / this time; the link is shared with the other tenants of the box)
+        dbuf = {k: torch.empty_like(v, device=device) for k, v in hring[0].items()}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(2):
+            ev0.record()
+            for _ in range(10):
+                for k, v in hring[0].items():
+                    dbuf[k].copy_(v, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+        h2d_ms = ev0.elapsed_time(ev1) / 10
+        del dbuf
 
-    def reduce_grads(_gs=None):
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
+        def reduce_grads(_gs=None):
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat)
 
-    if use_graph:
-        from closerlook3d_b200.graphed import PipelinedTrainer
-        b0 = ring[0]
-        tr = PipelinedTrainer(mod, b0["xyz"], b0["mask"], b0["features"], gout, after_step=reduce_grads)
-        for w in range(4):
-            tr.step(hring[w % len(hring)])
-        tr.flush()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for s in range(nst):
-            tr.step(hring[s % len(hring)])
-        tr.flush()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        how = "PipelinedTrainer: H2D of batch i+1 overlaps the replay of batch i; results read one step late"
-    else:
-        def e2e_step(hb):
-            out = step({k: v.to(device, non_blocking=True) for k, v in hb.items()})
-            return float(out.sum().item())  # D2H read of the step's result
-        for w in range(3):
-            e2e_step(hring[w % len(hring)])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for s in range(nst):
-            e2e_step(hring[s % len(hring)])
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        how = "serial: H2D, step, D2H"
+        if use_graph:
+            from closerlook3d_b200.graphed import PipelinedTrainer
+            b0 = ring[0]
+            tr = PipelinedTrainer(mod, b0["xyz"], b0["mask"], b0["features"], gout, after_step=reduce_grads)
+            for w in range(4):
+                tr.step(hring[w % len(hring)])
+            tr.flush()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for s in range(nst):
+                tr.step(hring[s % len(hring)])
+            tr.flush()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            how = "PipelinedTrainer: H2D of batch i+1 overlaps the replay of batch i; results read one step late"
+        else:
+            def e2e_step(hb):
+                out = step({k: v.to(device, non_blocking=True) for k, v in hb.items()})
+                return float(out.sum().item())  # D2H read of the step's result
+            for w in range(3):
+                e2e_step(hring[w % len(hring)])
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for s in range(nst):
+                e2e_step(hring[s % len(hring)])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            how = "serial: H2D, step, D2H"
     te = torch.tensor([dt], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": pts_per_step * nst / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": 4, "steps": nst, "how": how,
+           "pinned_buffers": "allocated on the GPU-local NUMA node" if nl.cpus else "default placement",
+           "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
            "timing": "host wall clock around all steps (copies inside), max over ranks"}
     return dict(value=value, ms_per_step=ms_per_step, clocks=clocks, launches=int(launches), prof=prof, e2e=e2e,
                 B_local=B_local, wall_s=t_wall, mod=mod, radius=radius, ring=ring)

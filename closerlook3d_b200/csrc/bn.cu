@@ -14,29 +14,31 @@ constexpr int kBnTile = 32;
 
 // mean / invstd from the partial sums; running-stat update as nn.BatchNorm1d (unbiased variance).
 // One CTA of 1024 threads handles 32 channels (32 tile-lanes each), deterministic.
+// One CTA = 8 channels (one 32-byte sector of a partial row) x 128 tile slices: C/8 CTAs, so the whole partial
+// array is in flight at once (the kernel sits on the forward's critical path and is pure load latency).
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int ntiles, int C,
                                                            double count, float eps, float momentum, int training,
                                                            float* __restrict__ running_mean,
                                                            float* __restrict__ running_var,
                                                            float* __restrict__ save_stats) {
-  __shared__ double s1[32][33], s2[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
+  __shared__ double s1[128][9], s2[128][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + tx;
   double a1 = 0.0, a2 = 0.0;
   if (training && c < C) {
     double b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
     int t = ty;
-    for (; t + 96 < ntiles; t += 128) {  // four independent load streams per thread
+    for (; t + 384 < ntiles; t += 512) {  // four independent load streams per thread
       a1 += (double)partial[((size_t)t * 2 + 0) * C + c];
       a2 += (double)partial[((size_t)t * 2 + 1) * C + c];
-      b1 += (double)partial[((size_t)(t + 32) * 2 + 0) * C + c];
-      b2 += (double)partial[((size_t)(t + 32) * 2 + 1) * C + c];
-      c1 += (double)partial[((size_t)(t + 64) * 2 + 0) * C + c];
-      c2 += (double)partial[((size_t)(t + 64) * 2 + 1) * C + c];
-      d1 += (double)partial[((size_t)(t + 96) * 2 + 0) * C + c];
-      d2 += (double)partial[((size_t)(t + 96) * 2 + 1) * C + c];
+      b1 += (double)partial[((size_t)(t + 128) * 2 + 0) * C + c];
+      b2 += (double)partial[((size_t)(t + 128) * 2 + 1) * C + c];
+      c1 += (double)partial[((size_t)(t + 256) * 2 + 0) * C + c];
+      c2 += (double)partial[((size_t)(t + 256) * 2 + 1) * C + c];
+      d1 += (double)partial[((size_t)(t + 384) * 2 + 0) * C + c];
+      d2 += (double)partial[((size_t)(t + 384) * 2 + 1) * C + c];
     }
-    for (; t < ntiles; t += 32) {
+    for (; t < ntiles; t += 128) {
       a1 += (double)partial[((size_t)t * 2 + 0) * C + c];
       a2 += (double)partial[((size_t)t * 2 + 1) * C + c];
     }
@@ -46,14 +48,17 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   s1[ty][tx] = a1;
   s2[ty][tx] = a2;
   __syncthreads();
+  // fixed-order tree over the 128 slices (deterministic)
+  for (int h = 64; h >= 1; h >>= 1) {
+    if (ty < h) {
+      s1[ty][tx] += s1[ty + h][tx];
+      s2[ty][tx] += s2[ty + h][tx];
+    }
+    __syncthreads();
+  }
   if (ty == 0 && c < C) {
     if (training) {
-      double sum = 0.0, sq = 0.0;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        sum += s1[i][tx];
-        sq += s2[i][tx];
-      }
+      const double sum = s1[0][tx], sq = s2[0][tx];
       const double mean = sum / count;
       double var = sq / count - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -242,7 +247,7 @@ extern "C" int cl3d_bn_finalize(const float* bn_partial, int ntiles, int C, long
   CL3D_REQUIRE(C >= 1 && save_stats, "cl3d_bn_finalize: bad arguments");
   CL3D_REQUIRE(!training || (bn_partial && ntiles >= 1 && count >= 1), "cl3d_bn_finalize: training needs partial sums");
   CL3D_REQUIRE(training || (running_mean && running_var), "cl3d_bn_finalize: eval needs running statistics");
-  bn_finalize_kernel<<<ceil_div(C, 32), 1024, 0, (cudaStream_t)stream_>>>(bn_partial, ntiles, C, (double)count, eps,
+  bn_finalize_kernel<<<ceil_div(C, 8), 1024, 0, (cudaStream_t)stream_>>>(bn_partial, ntiles, C, (double)count, eps,
                                                                          momentum, training, running_mean,
                                                                          running_var, save_stats); CL3D_LAUNCHED(1);
   return check_launch("bn_finalize_kernel");

@@ -55,6 +55,13 @@ __device__ __forceinline__ float ref_d2(float qx, float qy, float qz, float x, f
   return t;
 }
 
+// base + elem_off floats as ONE instruction (IMAD.WIDE.U32): the compiler otherwise rebuilds the 64-bit address
+// of a gathered row from two partial bases with four instructions (measured in the PointWiseMLP gather loops)
+__device__ __forceinline__ const float* row_at(const float* base, unsigned elem_off) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(elem_off), "l"(base));
+  return reinterpret_cast<const float*>(r);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_fwd_kernel(const PwArgs a
       float ap[CI], S[CI], S2[CI], m[CI];
       int km[CI];
       {
-        const float* arow = ab + (unsigned)s_idx[0];
+        const float* arow = row_at(ab, (unsigned)s_idx[0]);
 #pragma unroll
         for (int i = 0; i < CI; ++i) {
           ap[i] = __ldg(arow + 32 * i) - fmaf(wpz[i], qz, fmaf(wpy[i], qy, wpx[i] * qx));
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_fwd_kernel(const PwArgs a
         float v[kPWU][CI];
 #pragma unroll
         for (int u = 0; u < kPWU; ++u) {
-          const float* row = tb + (unsigned)s_idx[k0 + u];
+          const float* row = row_at(tb, (unsigned)s_idx[k0 + u]);
 #pragma unroll
           for (int i = 0; i < CI; ++i) v[u][i] = __ldg(row + 32 * i);  // lanes past the chunk read slack (unused)
         }
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_fwd_kernel(const PwArgs a
           }
       }
       for (; k0 < a.K; ++k0) {
-        const float* row = tb + (unsigned)s_idx[k0];
+        const float* row = row_at(tb, (unsigned)s_idx[k0]);
 #pragma unroll
         for (int i = 0; i < CI; ++i) {
           const float t = __ldg(row + 32 * i);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_dense_kernel(const Pw
           float v[kPWU][CI];
 #pragma unroll
           for (int u = 0; u < kPWU; ++u) {
-            const float* row = aq + __shfl_sync(0xffffffffu, myq, r + u);
+            const float* row = row_at(aq, __shfl_sync(0xffffffffu, myq, r + u));
 #pragma unroll
             for (int i = 0; i < CI; ++i) v[u][i] = __ldg(row + 32 * i);  // lanes past the chunk read slack (unused)
           }
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_dense_kernel(const Pw
             for (int i = 0; i < CI; ++i) acc[i] += v[u][i];
         }
         for (; r < rows; ++r) {
-          const float* row = aq + __shfl_sync(0xffffffffu, myq, r);
+          const float* row = row_at(aq, __shfl_sync(0xffffffffu, myq, r));
 #pragma unroll
           for (int i = 0; i < CI; ++i) acc[i] += __ldg(row + 32 * i);
         }

@@ -82,7 +82,8 @@ class PipelinedTrainer:
 
     def __init__(self, module, xyz, mask, features, grad_out, after_step=None):
         self.slots = [GraphedStep(module, xyz, mask, features, grad_out) for _ in range(2)]
-        self.copy = torch.cuda.Stream()
+        # high priority: its own hardware queue, so the H2D copies are never ordered behind the replay's kernels
+        self.copy = torch.cuda.Stream(priority=-1)
         self.after_step = after_step            # e.g. the gradient all-reduce + optimizer step
         self.result_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]     # replay i finished (its buffers are free again)
