@@ -437,11 +437,13 @@ inline bool tc_gemm_supported(const TcGemmArgs& g) {
 
 template <int NB, int AV, int BV>
 inline void tc_gemm_launch_k(const TcGemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;  // per device (the attribute is per device; one bit each)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_set >> (dev & 63)) & 1ull)) {
     cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, AV, BV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)tc_smem_bytes(NB == 3 ? 96 : NB == 5 ? 160 : 256));
-    attr_set = true;
+    attr_set |= 1ull << (dev & 63);
   }
   gemm_tf32x3_kernel<NB, AV, BV><<<grid, kTcThreads, smem, stream>>>(g);
 }

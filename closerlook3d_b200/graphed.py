@@ -108,7 +108,7 @@ class PipelinedTrainer:
         out = self.slots[slot].replay()
         if self.after_step is not None:
             self.after_step(self.slots[slot])
-        self.result_host[slot].copy_(out.sum().reshape(1), non_blocking=True)  # D2H of the step's result
+        self.result_host[slot].copy_(out.detach().sum().reshape(1), non_blocking=True)  # D2H of the step's result
         self.done[slot].record(cur)
         prev = None
         if self.pending is not None:
