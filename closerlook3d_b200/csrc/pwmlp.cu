@@ -330,8 +330,9 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_bwd_dense_kernel(const Pw
         if (okc[i]) {
           const float bv = sg[i] * __ldg(trow + 32 * i);
           const float dbv = -cnt * c1[i] - c2[i] * (acc[i] + cnt * (bv - mean[i]));
-          grow[a.Cop + c0 + lane + 32 * i] = (c0 + lane + 32 * i < a.Cout) ? sg[i] * dbv : 0.f;
-          grow[c0 + lane + 32 * i] = 0.f;
+          // grad_ab is zero-filled by the entry point; the query pass adds its arg-max hits to the same words
+          // concurrently, so this is a reduction too (one per word: no contention)
+          if (c0 + lane + 32 * i < a.Cout) atomicAdd(&grow[a.Cop + c0 + lane + 32 * i], sg[i] * dbv);
         }
       }
     }
@@ -587,13 +588,42 @@ extern "C" size_t cl3d_pwmlp_bwd_scratch_floats(int B, int N, int M, int Cout) {
   return part + (size_t)B * M * Cop + 64;
 }
 
+// fork/join events of cl3d_pwmlp_bwd: a small per-device ring of event sets, so that several calls can be in
+// flight (each call only orders its own streams; an event is reusable as soon as the waits on it are enqueued)
+struct PwEvents {
+  cudaEvent_t start, zeroed, stats, joined;
+};
+static PwEvents* pw_events() {
+  constexpr int kDevs = 64, kRing = 16;
+  static PwEvents ring[kDevs][kRing];
+  static bool made[kDevs] = {};
+  static unsigned next[kDevs] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kDevs) return nullptr;
+  if (!made[dev]) {
+    for (int i = 0; i < kRing; ++i) {
+      cudaEvent_t* e[4] = {&ring[dev][i].start, &ring[dev][i].zeroed, &ring[dev][i].stats, &ring[dev][i].joined};
+      for (auto p : e)
+        if (cudaEventCreateWithFlags(p, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    made[dev] = true;
+  }
+  return &ring[dev][next[dev]++ % kRing];
+}
+
 extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, const float* wp,
                               const float* sgn, const float* query_xyz, const int* idx, const int* csr_off,
                               const int* csr_ent, const float* ysel, const float* aq, const float* sq,
                               const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
                               int M, int K, int Cout, float radius, float* scratch, float* dgamma_dbeta,
-                              float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream_) {
+                              float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream_, cl3d_stream_t side_stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  // With a side stream the zero-fill of grad_ab and the latency-bound query pass run beside the statistics and
+  // the support-major gather (fork/join with events: capturable into a CUDA graph); without one, in order.
+  cudaStream_t side = side_stream_ ? (cudaStream_t)side_stream_ : stream;
+  const bool forked = side != stream;
+  PwEvents* ev = forked ? pw_events() : nullptr;
+  if (forked && !ev) return CL3D_ERR_LAUNCH;
   CL3D_REQUIRE(grad_out && out && ab_pm && wp && sgn && query_xyz && idx && csr_off && csr_ent && ysel && aq && sq &&
                    karg && save_stats && gamma && scratch && dgamma_dbeta && grad_ab_pm && grad_wp,
                "cl3d_pwmlp_bwd: null pointer");
@@ -611,11 +641,22 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   const size_t smem_s = (size_t)kPWTile * (Cop + 1) * sizeof(float);
   if (smem_s > 48 * 1024)
     cudaFuncSetAttribute(pwmlp_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+  if (forked) {
+    cudaEventRecord(ev->start, stream);
+    cudaStreamWaitEvent(side, ev->start, 0);
+  }
+  cudaMemsetAsync(grad_ab_pm, 0, sizeof(float) * (size_t)B * N * 2 * Cop, side);
+  if (forked) cudaEventRecord(ev->zeroed, side);
   pwmlp_bwd_stats_kernel<<<ntiles, 256, smem_s, stream>>>(grad_out, out, ysel, save_stats, gamma, Cout, Cop, M, partial,
                                                           dzs_pm);
   CL3D_LAUNCHED(1);
   int rc = cl3d_reduce_partials(partial, ntiles, 2 * Cout, dgamma_dbeta, stream_);  // (dgamma, dbeta)
   if (rc) return rc;
+  if (forked) {
+    cudaEventRecord(ev->stats, stream);
+    cudaStreamWaitEvent(side, ev->stats, 0);   // the query pass needs (dgamma, dbeta) and sc*dz
+    cudaStreamWaitEvent(stream, ev->zeroed, 0);  // the gather pass needs the zero-filled grad_ab
+  }
   PwArgs a = {};
   a.ab_pm = ab_pm; a.wp = wp; a.sgn = sgn; a.query_xyz = query_xyz; a.idx = idx;
   a.ysel = const_cast<float*>(ysel); a.aq = const_cast<float*>(aq); a.sq = const_cast<float*>(sq);
@@ -638,9 +679,14 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   if (rc) return rc;
   CL3D_REQUIRE(Cop / 4 <= 256, "cl3d_pwmlp_bwd: Cout > 1024 unsupported");
   const int ny = 256 / (Cop / 4);
-  pwmlp_bwd_query_kernel<<<gqy, ny * (Cop / 4), (size_t)ny * 3 * Cop * sizeof(float), stream>>>(a, (long long)B * M);
+  pwmlp_bwd_query_kernel<<<gqy, ny * (Cop / 4), (size_t)ny * 3 * Cop * sizeof(float), side>>>(a, (long long)B * M);
   CL3D_LAUNCHED(1);
   rc = check_launch("pwmlp_bwd_query_kernel");
   if (rc) return rc;
-  return cl3d_reduce_partials(partial, gqy, 3 * Cout, grad_wp, stream_);
+  rc = cl3d_reduce_partials(partial, gqy, 3 * Cout, grad_wp, (cl3d_stream_t)side);
+  if (forked) {
+    cudaEventRecord(ev->joined, side);
+    cudaStreamWaitEvent(stream, ev->joined, 0);
+  }
+  return rc;
 }

@@ -1,5 +1,7 @@
 """Thin tensor-level wrappers over the C ABI (include/cl3d.h): allocate outputs/workspaces with torch,
 pass raw device pointers + the current CUDA stream.  No computation happens in Python."""
+import ctypes
+
 import torch
 
 from . import _lib
@@ -270,8 +272,9 @@ def pwmlp_fwd_out(ysel, stats, gamma, beta):
 
 
 def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, ysel, aq, sq, karg, stats, gamma,
-              radius):
-    """-> (grad_ab_pm (B,N,2Cop), grad_wp (3,Cout), dgamma (Cout), dbeta (Cout))"""
+              radius, side_stream=None):
+    """-> (grad_ab_pm (B,N,2Cop), grad_wp (3,Cout), dgamma (Cout), dbeta (Cout)); side_stream: a torch stream the
+    library may fork onto (zero-fill + query pass run beside the gather pass), joined before it returns"""
     B, N, C2 = ab_pm.shape
     Cout, M, K = out.shape[1], out.shape[2], idx.shape[2]
     L = _lib.lib()
@@ -283,7 +286,8 @@ def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, y
     check(L.cl3d_pwmlp_bwd(ptr(grad_out), ptr(out), ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(idx),
                            ptr(csr_off), ptr(csr_ent), ptr(ysel), ptr(aq), ptr(sq), ptr(karg), ptr(stats), ptr(gamma),
                            B, N, M, K, Cout, float(radius), ptr(partial), ptr(dgb), ptr(grad_ab), ptr(grad_wp),
-                           stream_ptr()), "cl3d_pwmlp_bwd")
+                           stream_ptr(), ctypes.c_void_p(side_stream.cuda_stream) if side_stream is not None else None),
+          "cl3d_pwmlp_bwd")
     return grad_ab, grad_wp, dgb[0], dgb[1]
 
 

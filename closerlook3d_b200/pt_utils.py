@@ -103,11 +103,13 @@ _SIDE = {}
 overlap_enabled = True  # run the neighbour search on a side stream (fork/join), see NeighborList
 
 
-def _side_stream(device):
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+def _side_stream(device, priority=0):
+    """per-device helper stream; priority=-1: a second, high-priority one (its CTAs are scheduled first when it
+    and the main stream both have a kernel pending -- used for short latency-bound passes beside a long one)"""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), priority)
     st = _SIDE.get(key)
     if st is None:
-        st = torch.cuda.Stream(device=device)
+        st = torch.cuda.Stream(device=device, priority=priority)
         _SIDE[key] = st
     return st
 

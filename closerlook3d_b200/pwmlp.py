@@ -51,8 +51,10 @@ class _FusedPointWiseMLP(Function):
             raise NotImplementedError("PointWiseMLP backward in eval mode (running statistics) is not fused")
         nl = ctx.nl
         off, ent = nl.csr_all_slots()
+        side = pt_utils._side_stream(out.device, priority=-1) if pt_utils.overlap_enabled else None
         grad_ab, grad_wp, dgamma, dbeta = ops.pwmlp_bwd(grad_out.contiguous(), out, ab_pm, wp, sgn, query_xyz, nl.idx,
-                                                        off, ent, ysel, aq, sq, karg, stats, bn_weight, ctx.radius)
+                                                        off, ent, ysel, aq, sq, karg, stats, bn_weight, ctx.radius,
+                                                        side_stream=side)
         P = B * N
         Cp = ops.padded_channels(C)
         # the two products of the backward are independent: the weight gradient runs on the side stream

@@ -225,7 +225,9 @@ int cl3d_sgemm_algo(const float* a, long long sa_m, long long sa_k, const float*
  * fwd_out   : out (B,Cout,M) = relu(sc*ysel + sh).
  * bwd       : csr_off/csr_ent = cl3d_build_csr over ALL K slots (ncount = K); scratch =
  *             cl3d_pwmlp_bwd_scratch_floats(...) floats; dgamma_dbeta (2,Cout); grad_ab_pm (B,N,2*Cop) fully
- *             written (dense part + d/dA stored by the support-major pass, arg-max hits added with fp32 red.add);
+ *             written (zero-filled, then the support-major pass and the query pass add their parts with fp32
+ *             red.add); side_stream (may be NULL): the zero-fill and the query pass run on it beside the other
+ *             two passes, forked from and joined back into `stream` with events (CUDA-graph capturable);
  *             grad_wp (3,Cout) = the -sum da' (x) q/r part of d/dWp (the rest comes out of the weight-gradient
  *             product). */
 size_t cl3d_pwmlp_bwd_scratch_floats(int B, int N, int M, int Cout);
@@ -247,7 +249,7 @@ int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, 
                    const int* csr_ent, const float* ysel, const float* aq, const float* sq,
                    const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
                    int M, int K, int Cout, float radius, float* scratch, float* dgamma_dbeta,
-                   float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream);
+                   float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream, cl3d_stream_t side_stream);
 
 #ifdef __cplusplus
 }
