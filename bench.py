@@ -68,8 +68,42 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nv = []          # (sm_mhz, sm_max_mhz, reasons bitmask) sampled through NVML every ~5 ms
+        self.nv_stop = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _nvml_loop(self, nv, h, stop):
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not stop.is_set():
+            try:
+                self.nv.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx), int(reasons(h))))
+            except Exception:
+                break
+            stop.wait(0.005)
 
     def start(self):
+        # the timed region of a default run is ~15 ms: nvidia-smi's polling loop (first line after >100 ms) often
+        # misses it, so the clocks are sampled through NVML in a thread; nvidia-smi stays as the fallback
+        try:
+            nv, h = self._nvml_handle()
+            self.nv_stop = threading.Event()
+            self.nvt = threading.Thread(target=self._nvml_loop, args=(nv, h, self.nv_stop), daemon=True)
+            self.nvt.start()
+        except Exception:
+            self.nv_stop = None
+        if self.nv_stop is not None:
+            return   # no nvidia-smi next to NVML: eight polling nvidia-smi processes (one per rank) contend for the
+            #          driver and stalled kernel launches -- the 8-GPU step time doubled (profiles/RESULTS_r1.md)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,6 +118,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv_stop is not None:
+            self.nv_stop.set()
+            self.nvt.join(timeout=1)
+            if self.nv:
+                if self.proc is not None:
+                    self.proc.terminate()
+                bits = 0
+                for _, _, r in self.nv:
+                    bits |= r
+                # nvmlClocksEventReason*: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+                names = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                         (0x4, "sw_power_cap")]
+                return {"sm_mhz": statistics.median(x[0] for x in self.nv), "sm_max_mhz": max(x[1] for x in self.nv),
+                        "samples": len(self.nv), "reasons": sorted(n for b, n in names if bits & b), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
