@@ -147,7 +147,8 @@ def _gloo_worker(rank, world, port, q):
     x = torch.arange(40, dtype=torch.float32).view(10, 4)[lo:hi]
     w(x).sum().backward()
     cdist.allreduce_gradients(list(w.parameters()), average=False)
-    q.put((rank, lo, hi, w.weight.grad.clone(), w.bias.grad.clone()))
+    # plain lists: a tensor would travel as a shared-memory handle that dies with this process
+    q.put((rank, lo, hi, w.weight.grad.tolist(), w.bias.grad.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -167,4 +168,4 @@ def test_data_parallel_plumbing_gloo_world2():
     w = torch.nn.Linear(4, 3)
     w(torch.arange(40, dtype=torch.float32).view(10, 4)).sum().backward()
     for r in res:
-        assert torch.allclose(r[3], w.weight.grad) and torch.allclose(r[4], w.bias.grad)
+        assert torch.allclose(torch.tensor(r[3]), w.weight.grad) and torch.allclose(torch.tensor(r[4]), w.bias.grad)
