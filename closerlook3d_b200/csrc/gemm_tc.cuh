@@ -23,6 +23,8 @@
 // output row / column, which is never stored.  Only the k tail is zero-filled.
 // With gridDim.z > 1 the k range is divided among CTAs (split-K) and reduced afterwards in a fixed order.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cl3d {
@@ -437,13 +439,13 @@ inline bool tc_gemm_supported(const TcGemmArgs& g) {
 
 template <int NB, int AV, int BV>
 inline void tc_gemm_launch_k(const TcGemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
-  static unsigned long long attr_set = 0;  // per device (the attribute is per device; one bit each)
+  static std::atomic<unsigned long long> attr_set{0};  // per device (the attribute is per device; one bit each)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!((attr_set >> (dev & 63)) & 1ull)) {
+  if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
     cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, AV, BV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)tc_smem_bytes(NB == 3 ? 96 : NB == 5 ? 160 : 256));
-    attr_set |= 1ull << (dev & 63);
+    attr_set.fetch_or(1ull << (dev & 63));
   }
   gemm_tf32x3_kernel<NB, AV, BV><<<grid, kTcThreads, smem, stream>>>(g);
 }

@@ -20,6 +20,8 @@
 //                           cnt_j and sum_e a'[q_e]  -> one row gather, 2 instructions per element, no atomics
 //   pwmlp_bwd_query_kernel  thread per (query, 4 channels), no K loop: d/da' in closed form from the saved S,
 //                           d/dA[j_0] as one red.global.add.v4.f32, the arg-max slot's sc*dz, d/dWp partials
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cl3d {
@@ -598,6 +600,8 @@ static PwEvents* pw_events() {
   static PwEvents ring[kDevs][kRing];
   static bool made[kDevs] = {};
   static unsigned next[kDevs] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kDevs) return nullptr;
   if (!made[dev]) {
