@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host helpers for libcl3d (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -29,6 +30,14 @@ int check_launch(const char* what);
     }                                      \
   } while (0)
 
+// true exactly once per CUDA device (host side; for per-device one-time settings such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize, which is a per-device attribute)
+inline bool first_call_on_device(std::atomic<unsigned long long>& seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (seen.fetch_or(bit) & bit) == 0;
+}
 __host__ __device__ inline int padded_channels(int C) { return (C + 7) & ~7; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

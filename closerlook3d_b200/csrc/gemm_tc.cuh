@@ -439,14 +439,10 @@ inline bool tc_gemm_supported(const TcGemmArgs& g) {
 
 template <int NB, int AV, int BV>
 inline void tc_gemm_launch_k(const TcGemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
-  static std::atomic<unsigned long long> attr_set{0};  // per device (the attribute is per device; one bit each)
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
+  static std::atomic<unsigned long long> attr_set{0};
+  if (first_call_on_device(attr_set))
     cudaFuncSetAttribute(gemm_tf32x3_kernel<NB, AV, BV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)tc_smem_bytes(NB == 3 ? 96 : NB == 5 ? 160 : 256));
-    attr_set.fetch_or(1ull << (dev & 63));
-  }
   gemm_tf32x3_kernel<NB, AV, BV><<<grid, kTcThreads, smem, stream>>>(g);
 }
 

@@ -684,11 +684,9 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
     // queries per CTA: 64 (8 per warp) amortises the cloud load; fewer when that would leave SMs idle
     int qpc = 64;
     while (qpc > 8 && (long long)B * ceil_div(M, qpc) < 6LL * sm_count()) qpc >>= 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_brute{0};
+    if (first_call_on_device(attr_brute))
       cudaFuncSetAttribute(ball_query_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
     dim3 grid(ceil_div(M, qpc), B);
     ball_query_brute_kernel<<<grid, kBQWarps * 32, smem, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
                                                                    N, M, radius, K, qpc, idx, idx_mask, ncount); CL3D_LAUNCHED(1);
@@ -718,11 +716,9 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
   cell_fill_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_start, cell_rank,
                                                                   sorted); CL3D_LAUNCHED(1);
   size_t smem = (size_t)kBQWarps * (kCandCap + cap3k) * 8 + (size_t)kBQWarps * K * 4;
-  static bool attr_set2 = false;
-  if (!attr_set2) {
+  static std::atomic<unsigned long long> attr_grid{0};
+  if (first_call_on_device(attr_grid))
     cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set2 = true;
-  }
   const long long total = (long long)B * M;
   ball_query_grid_kernel<<<(unsigned)((total + kBQWarps - 1) / kBQWarps), kBQWarps * 32, smem, stream>>>(
       query_xyz, support_xyz, query_mask, params, cell_start, sorted, B, N, M, radius, K, cap, idx, idx_mask, ncount); CL3D_LAUNCHED(1);
