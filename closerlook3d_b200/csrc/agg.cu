@@ -860,8 +860,8 @@ static int launch_fwd(const AggArgs& a, cudaStream_t stream) {
   const int nchunks = ceil_div(a.Cp, 32 * CI);
   const SmemLayout L = smem_layout(32 * CI, 0);
   const size_t smem = L.total + (FAM == CL3D_FAM_PSEUDOGRID ? (size_t)kMaxKP * 32 * CI * sizeof(float) : 0);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(agg_fwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> seen{0};
+  allow_big_smem(agg_fwd_kernel<FAM, CI>, seen);
   dim3 grid(a.ntiles, nchunks);
   agg_fwd_kernel<FAM, CI><<<grid, kAggWarps * 32, smem, stream>>>(a);
   CL3D_LAUNCHED(1);
@@ -874,8 +874,8 @@ static int launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   const int ppc = params_per_channel<FAM>(a.nkp);
   const SmemLayout L = smem_layout(32 * CI, ppc * 32 * CI);
   const size_t smem = L.total + (FAM == CL3D_FAM_PSEUDOGRID ? pg_bwd_extra_floats(CI) * sizeof(float) : 0);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(agg_bwd_kernel<FAM, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> seen{0};
+  allow_big_smem(agg_bwd_kernel<FAM, CI>, seen);
   dim3 grid(grid_x, nchunks);
   agg_bwd_kernel<FAM, CI><<<grid, kAggWarps * 32, smem, stream>>>(a);
   CL3D_LAUNCHED(1);
@@ -910,12 +910,12 @@ static int launch_sincos(const AggArgs& a, bool bwd, int grid_x, cudaStream_t st
   const SmemLayout L = smem_layout(2 * 32 * PI, 0);
   dim3 grid(grid_x, ceil_div(npairs, 32 * PI));
   if (!bwd) {
-    if (L.total > 48 * 1024)
-      cudaFuncSetAttribute(sincos_fwd_kernel<PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    static std::atomic<unsigned long long> seen{0};
+    allow_big_smem(sincos_fwd_kernel<PI>, seen);
     sincos_fwd_kernel<PI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
   } else {
-    if (L.total > 48 * 1024)
-      cudaFuncSetAttribute(sincos_bwd_kernel<PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    static std::atomic<unsigned long long> seen{0};
+    allow_big_smem(sincos_bwd_kernel<PI>, seen);
     sincos_bwd_kernel<PI><<<grid, kAggWarps * 32, L.total, stream>>>(a);
   }
   CL3D_LAUNCHED(1);
@@ -953,7 +953,7 @@ static int dispatch_bwd(int family, int ci, const AggArgs& a, int gx, cudaStream
 }
 
 static int bwd_grid_x(int ntiles) {
-  const int cap = sm_count() * 4;
+  const int cap = persistent_grid_cap();
   return ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap;
 }
 

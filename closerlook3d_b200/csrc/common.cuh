@@ -38,11 +38,20 @@ inline bool first_call_on_device(std::atomic<unsigned long long>& seen) {
   const unsigned long long bit = 1ull << (dev & 63);
   return (seen.fetch_or(bit) & bit) == 0;
 }
+// Opt a kernel into the full dynamic shared-memory carve-out (227 KB) ONCE per device instead of calling
+// cudaFuncSetAttribute on every launch.  `seen` must be a static per kernel instantiation.
+constexpr int kMaxDynSmem = 227 * 1024;
+template <typename K>
+inline void allow_big_smem(K kernel, std::atomic<unsigned long long>& seen) {
+  if (first_call_on_device(seen))
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
 __host__ __device__ inline int padded_channels(int C) { return (C + 7) & ~7; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
+int persistent_grid_cap();  // 4 x SMs (test hook: CL3D_TEST_MAX_GRID)
 
 // number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
 void count_launches(int n);

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cl3d {
@@ -36,6 +38,18 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// Grid size of the persistent (tile-loop) kernels: 4 CTAs per SM.  CL3D_TEST_MAX_GRID (read on every call, tests
+// only) caps it so that small inputs run several tiles per CTA.
+int persistent_grid_cap() {
+  int cap = sm_count() * 4;
+  const char* e = getenv("CL3D_TEST_MAX_GRID");
+  if (e && *e) {
+    const int v = atoi(e);
+    if (v >= 1 && v < cap) cap = v;
+  }
+  return cap;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -115,8 +115,8 @@ template <int CI>
 static int launch_pool_fwd(const float* feat_pm, const int* idx, int B, int N, int M, int K, int C, int Cp, float* out,
                            unsigned char* arg, cudaStream_t stream) {
   const size_t smem = align_up((size_t)kPoolWarps * K * 4, 16) + (size_t)32 * CI * (kPoolTile + 1) * 4;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(gather_max_fwd_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> seen{0};
+  allow_big_smem(gather_max_fwd_kernel<CI>, seen);
   dim3 grid(B * ceil_div(M, kPoolTile), ceil_div(Cp, 32 * CI));
   gather_max_fwd_kernel<CI><<<grid, kPoolWarps * 32, smem, stream>>>(feat_pm, idx, N, M, K, C, Cp, out, arg);
   CL3D_LAUNCHED(1);
@@ -153,8 +153,8 @@ extern "C" int cl3d_gather_max_bwd(const float* grad_out, const int* idx, const 
   const int Cp = padded_channels(C);
   cudaMemsetAsync(grad_pm, 0, sizeof(float) * (size_t)B * N * Cp, stream);
   const size_t smem = (size_t)32 * (C + 1) * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(gather_max_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> seen{0};
+  allow_big_smem(gather_max_bwd_kernel, seen);
   gather_max_bwd_kernel<<<B * ceil_div(M, 32), 256, smem, stream>>>(grad_out, idx, arg, N, M, K, C, Cp, grad_pm);
   CL3D_LAUNCHED(1);
   return check_launch("gather_max_bwd_kernel");

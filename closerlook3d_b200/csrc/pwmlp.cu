@@ -5,6 +5,9 @@
 //     y[o,q,k] = Wp[o]·dp_k + Wc[o]·f_i + Wr[o]·(f_{j_k} - f_i),     f_i = f of slot 0 (nearest neighbour)
 // and dp_k = (s_{j_k} - q)/r is a difference, so y separates into a per-QUERY and a per-POINT term:
 //     y[o,q,k] = a'[q][o] + bv[j_k][o],   a'[q] = (Wc-Wr) f_{j_0} - Wp q/r,   bv[j] = Wr f_j + Wp s_j/r .
+// Both positions are taken relative to the cloud's first support point o_b (q - o_b, s - o_b: the difference is
+// unchanged), so the two terms that cancel stay of the size of the cloud's extent / r even for scenes far from the
+// coordinate origin (S3DIS rooms: |xyz| / r ~ 300 would cost 2e-5 of dp in fp32).
 // The per-point terms are ONE (B*N x (C+3)) x ((C+3) x 2*Cop) product over the augmented point-major matrix
 // [f | s/r] (csrc/gemm.cu); the per-neighbour work that remains is a row gather with 6 instructions per
 // element.  BatchNorm2d statistics over all B*M*K positions (padding slots included, as in the reference) are
@@ -36,6 +39,7 @@ struct PwArgs {
   const float* wp;           // (Cout,3)
   const float* sgn;          // (Cout) +1 / -1
   const float* query_xyz;    // (B,M,3)
+  const float* support_xyz;  // (B,N,3): row 0 of each cloud is the origin the separable terms are centred on
   const int* idx;            // (B,M,K)
   float* ysel;               // (B,Cout,M)
   float* aq;                 // (B,M,Cop) a'
@@ -119,8 +123,10 @@ __global__ void __launch_bounds__(kPWWarps * 32) pwmlp_fwd_kernel(const PwArgs a
         for (int k = lane; k < a.K; k += 32) s_idx[k] = (int)((unsigned)a.idx[gq * a.K + k] * rstride);  // row offsets
       }
       // a' = A[j_0] - Wp q/r      (slot 0 = nearest neighbour, reference :290)
-      const float qx = __fmul_rn(a.query_xyz[gq * 3 + 0], a.inv_radius), qy = __fmul_rn(a.query_xyz[gq * 3 + 1], a.inv_radius),
-                  qz = __fmul_rn(a.query_xyz[gq * 3 + 2], a.inv_radius);
+      const float* org = a.support_xyz + (size_t)b * a.N * 3;
+      const float qx = __fmul_rn(__fsub_rn(a.query_xyz[gq * 3 + 0], org[0]), a.inv_radius),
+                  qy = __fmul_rn(__fsub_rn(a.query_xyz[gq * 3 + 1], org[1]), a.inv_radius),
+                  qz = __fmul_rn(__fsub_rn(a.query_xyz[gq * 3 + 2], org[2]), a.inv_radius);
       __syncwarp();
       float ap[CI], S[CI], S2[CI], m[CI];
       int km[CI];
@@ -381,8 +387,10 @@ __global__ void __launch_bounds__(256) pwmlp_bwd_query_kernel(const PwArgs a, lo
       const uchar4 ks = *reinterpret_cast<const uchar4*>(a.karg + o);
       const int* irow = a.idx + gq * a.K;
       const int j0 = irow[0];
-      const float qx = __fmul_rn(a.query_xyz[gq * 3 + 0], a.inv_radius), qy = __fmul_rn(a.query_xyz[gq * 3 + 1], a.inv_radius),
-                  qz = __fmul_rn(a.query_xyz[gq * 3 + 2], a.inv_radius);
+      const float* org = a.support_xyz + (size_t)b * a.N * 3;
+      const float qx = __fmul_rn(__fsub_rn(a.query_xyz[gq * 3 + 0], org[0]), a.inv_radius),
+                  qy = __fmul_rn(__fsub_rn(a.query_xyz[gq * 3 + 1], org[1]), a.inv_radius),
+                  qz = __fmul_rn(__fsub_rn(a.query_xyz[gq * 3 + 2], org[2]), a.inv_radius);
       const float apv[4] = {ap.x, ap.y, ap.z, ap.w}, sbv[4] = {sb.x, sb.y, sb.z, sb.w}, dzv[4] = {dz.x, dz.y, dz.z, dz.w};
       const int ksv[4] = {ks.x, ks.y, ks.z, ks.w};
       float* gab = a.grad_ab_pm + (size_t)b * a.N * 2 * a.Cop;
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(256) pwmlp_bwd_query_kernel(const PwArgs a, lo
   }
 }
 
-// (B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | xyz*inv_r | 0...], Cpa = padded(C+3)
+// (B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | (xyz - xyz[b,0])*inv_r | 0...], Cpa = padded(C+3)
 __global__ void __launch_bounds__(256) to_point_major_aug_kernel(const float* __restrict__ in, const float* __restrict__ xyz,
                                                                  int C, int N, int Cpa, float inv_r,
                                                                  float* __restrict__ out) {
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(256) to_point_major_aug_kernel(const float* __
     float v = 0.f;
     if (n < N) {
       if (c < C) v = in[(size_t)c * N + n];
-      else if (c < C + 3) v = __fmul_rn(xyz[(size_t)n * 3 + (c - C)], inv_r);
+      else if (c < C + 3) v = __fmul_rn(__fsub_rn(xyz[(size_t)n * 3 + (c - C)], xyz[c - C]), inv_r);
     }
     tile[r][tx] = v;
   }
@@ -490,7 +498,8 @@ template <int CI>
 static int launch_pw_fwd(const PwArgs& a, cudaStream_t stream) {
   const size_t smem = align_up((size_t)kPWWarps * a.K * 4, 16) + (size_t)32 * CI * (kPWTile + 1) * 4 +
                       (size_t)kPWWarps * 2 * 32 * CI * 4;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(pwmlp_fwd_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> seen{0};
+  allow_big_smem(pwmlp_fwd_kernel<CI>, seen);
   dim3 grid(a.ntiles, ceil_div(a.Cop, 32 * CI));
   pwmlp_fwd_kernel<CI><<<grid, kPWWarps * 32, smem, stream>>>(a);
   CL3D_LAUNCHED(1);
@@ -506,7 +515,7 @@ static int launch_pw_bwd(const PwArgs& a, int ntiles_n, int gx, cudaStream_t str
 }
 
 static int pw_dense_grid(int ntiles_n) {
-  int gx = sm_count() * 4;
+  int gx = persistent_grid_cap();
   return gx > ntiles_n ? ntiles_n : gx;
 }
 static int pw_query_grid(int B, int M, int Cop) {
@@ -549,15 +558,16 @@ extern "C" int cl3d_pwmlp_weight_grad(const float* gwcat, const float* grad_wp, 
 }
 
 extern "C" int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* sgn, const float* query_xyz,
-                                    const int* idx, int B, int N, int M, int K, int Cout, float radius, float* ysel,
+                                    const float* support_xyz, const int* idx, int B, int N, int M, int K, int Cout,
+                                    float radius, float* ysel,
                                     float* aq, float* sq, unsigned char* karg, float* bn_partial,
                                     cl3d_stream_t stream_) {
-  CL3D_REQUIRE(ab_pm && wp && sgn && query_xyz && idx && ysel && aq && sq && karg && bn_partial,
+  CL3D_REQUIRE(ab_pm && wp && sgn && query_xyz && support_xyz && idx && ysel && aq && sq && karg && bn_partial,
                "cl3d_pwmlp_fwd_stats: null pointer");
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 1 && K >= 1 && K <= 255 && Cout >= 1, "cl3d_pwmlp_fwd_stats: bad sizes (K <= 255)");
   if (B == 0) return CL3D_OK;
   PwArgs a = {};
-  a.ab_pm = ab_pm; a.wp = wp; a.sgn = sgn; a.query_xyz = query_xyz; a.idx = idx;
+  a.ab_pm = ab_pm; a.wp = wp; a.sgn = sgn; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx;
   a.ysel = ysel; a.aq = aq; a.sq = sq; a.karg = karg; a.partial = bn_partial;
   a.B = B; a.N = N; a.M = M; a.K = K; a.Cout = Cout; a.Cop = padded_channels(Cout);
   a.inv_radius = 1.0f / radius;
@@ -616,11 +626,12 @@ static PwEvents* pw_events() {
 }
 
 extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, const float* wp,
-                              const float* sgn, const float* query_xyz, const int* idx, const int* csr_off,
-                              const int* csr_ent, const float* ysel, const float* aq, const float* sq,
+                              const float* sgn, const float* query_xyz, const float* support_xyz, const int* idx,
+                              const int* csr_off, const int* csr_ent, const float* ysel, const float* aq, const float* sq,
                               const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
-                              int M, int K, int Cout, float radius, float* scratch, float* dgamma_dbeta,
-                              float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream_, cl3d_stream_t side_stream_) {
+                              int M, int K, int Cout, float radius, int training, float* scratch,
+                              float* dgamma_dbeta, float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream_,
+                              cl3d_stream_t side_stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   // With a side stream the zero-fill of grad_ab and the latency-bound query pass run beside the statistics and
   // the support-major gather (fork/join with events: capturable into a CUDA graph); without one, in order.
@@ -628,9 +639,10 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   const bool forked = side != stream;
   PwEvents* ev = forked ? pw_events() : nullptr;
   if (forked && !ev) return CL3D_ERR_LAUNCH;
-  CL3D_REQUIRE(grad_out && out && ab_pm && wp && sgn && query_xyz && idx && csr_off && csr_ent && ysel && aq && sq &&
+  CL3D_REQUIRE(grad_out && out && ab_pm && wp && sgn && query_xyz && support_xyz && idx && ysel && aq && sq &&
                    karg && save_stats && gamma && scratch && dgamma_dbeta && grad_ab_pm && grad_wp,
                "cl3d_pwmlp_bwd: null pointer");
+  CL3D_REQUIRE(!training || (csr_off && csr_ent), "cl3d_pwmlp_bwd: training mode needs the all-slots CSR lists");
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 1 && K >= 1 && K <= 255 && Cout >= 1, "cl3d_pwmlp_bwd: bad sizes");
   if (B == 0) return CL3D_OK;
   const int ntiles = B * ceil_div(M, kPWTile);
@@ -643,8 +655,8 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   float* partial = scratch;
   float* dzs_pm = scratch + ((part + 63) / 64) * 64;
   const size_t smem_s = (size_t)kPWTile * (Cop + 1) * sizeof(float);
-  if (smem_s > 48 * 1024)
-    cudaFuncSetAttribute(pwmlp_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+  static std::atomic<unsigned long long> seen_stats{0};
+  allow_big_smem(pwmlp_bwd_stats_kernel, seen_stats);
   if (forked) {
     cudaEventRecord(ev->start, stream);
     cudaStreamWaitEvent(side, ev->start, 0);
@@ -662,7 +674,7 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
     cudaStreamWaitEvent(stream, ev->zeroed, 0);  // the gather pass needs the zero-filled grad_ab
   }
   PwArgs a = {};
-  a.ab_pm = ab_pm; a.wp = wp; a.sgn = sgn; a.query_xyz = query_xyz; a.idx = idx;
+  a.ab_pm = ab_pm; a.wp = wp; a.sgn = sgn; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx;
   a.ysel = const_cast<float*>(ysel); a.aq = const_cast<float*>(aq); a.sq = const_cast<float*>(sq);
   a.karg = const_cast<unsigned char*>(karg);
   a.partial = partial;
@@ -672,15 +684,19 @@ extern "C" int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const flo
   a.dzs_pm = dzs_pm;
   a.B = B; a.N = N; a.M = M; a.K = K; a.Cout = Cout; a.Cop = Cop;
   a.inv_radius = 1.0f / radius;
-  a.inv_count = 1.0f / (float)((double)B * M * K);
+  // eval mode (frozen BatchNorm): the batch-statistics terms c1, c2 vanish (inv_count = 0 zeroes them in the query
+  // pass) and the dense support-major pass would add exact zeros, so it is not launched
+  a.inv_count = training ? 1.0f / (float)((double)B * M * K) : 0.f;
   a.ntiles = ntiles;
-  switch (pw_ci(Cop)) {
-    case 1: rc = launch_pw_bwd<1>(a, ntn, gx, stream); break;
-    case 2: rc = launch_pw_bwd<2>(a, ntn, gx, stream); break;
-    case 3: rc = launch_pw_bwd<3>(a, ntn, gx, stream); break;
-    default: rc = launch_pw_bwd<4>(a, ntn, gx, stream); break;
+  if (training) {
+    switch (pw_ci(Cop)) {
+      case 1: rc = launch_pw_bwd<1>(a, ntn, gx, stream); break;
+      case 2: rc = launch_pw_bwd<2>(a, ntn, gx, stream); break;
+      case 3: rc = launch_pw_bwd<3>(a, ntn, gx, stream); break;
+      default: rc = launch_pw_bwd<4>(a, ntn, gx, stream); break;
+    }
+    if (rc) return rc;
   }
-  if (rc) return rc;
   CL3D_REQUIRE(Cop / 4 <= 256, "cl3d_pwmlp_bwd: Cout > 1024 unsupported");
   const int ny = 256 / (Cop / 4);
   pwmlp_bwd_query_kernel<<<gqy, ny * (Cop / 4), (size_t)ny * 3 * Cop * sizeof(float), side>>>(a, (long long)B * M);

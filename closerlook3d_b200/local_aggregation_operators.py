@@ -308,4 +308,8 @@ class LocalAggregation(nn.Module):
     def forward(self, query_xyz, support_xyz, query_mask, support_mask, support_features):
         """query_xyz (B,M,3), support_xyz (B,N,3), masks (B,M)/(B,N) int32, support_features (B,C_in,N)
         -> (B,C_out,M)   (reference :452-464)"""
+        if support_features.is_cuda and support_features.device.index != torch.cuda.current_device():
+            with torch.cuda.device(support_features.device):  # streams / launches belong to the tensors' device
+                return self.local_aggregation_operator(query_xyz, support_xyz, query_mask, support_mask,
+                                                       support_features)
         return self.local_aggregation_operator(query_xyz, support_xyz, query_mask, support_mask, support_features)

@@ -11,6 +11,28 @@ I32 = torch.int32
 F32 = torch.float32
 
 
+def _on_device(fn):
+    """Run `fn` with the CUDA device of its tensor arguments current (kernels, the stream passed to the library and
+    the per-device attributes all belong to the CURRENT device), and refuse operands spread over several devices
+    (the reference's ops have the same single-device contract)."""
+    import functools
+
+    @functools.wraps(fn)
+    def call(*args, **kw):
+        dev = None
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RuntimeError(f"{fn.__name__}: operands on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return call
+
+
 def padded_channels(C):
     return (C + 7) & ~7
 
@@ -23,6 +45,7 @@ def _empty_pm(B, N, W, device):
     return torch.empty(B * N * W + PM_SLACK, dtype=F32, device=device)[:B * N * W].view(B, N, W)
 
 
+@_on_device
 def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_mask=True, want_ncount=True,
                algo=0):
     """-> (idx (B,M,K) i32, idx_mask (B,M,K) i32 | None, ncount (B,M) i32 | None); bit-exact with the
@@ -47,6 +70,7 @@ def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample
     return idx, idx_mask, ncount
 
 
+@_on_device
 def nearest_query(query_xyz, support_xyz, query_mask, support_mask):
     """-> (idx (B,M) i32, idx_mask (B,M) i32)  (masked_nearest_query_gpu.cu:8-62)"""
     require_cuda(query_xyz, "query_xyz", F32)
@@ -62,6 +86,7 @@ def nearest_query(query_xyz, support_xyz, query_mask, support_mask):
     return idx, idx_mask
 
 
+@_on_device
 def build_csr(idx, ncount, N):
     """transposed neighbour lists -> (csr_off (B,N+1) i32, csr_ent (B,M*K) i32)"""
     B, M, K = idx.shape
@@ -76,6 +101,7 @@ def build_csr(idx, ncount, N):
     return off, ent
 
 
+@_on_device
 def to_point_major(x_cn):
     """(B,C,N) -> (B,N,Cp) zero-padded rows"""
     require_cuda(x_cn, "features", F32)
@@ -85,6 +111,7 @@ def to_point_major(x_cn):
     return out
 
 
+@_on_device
 def to_channel_major(x_nc, C):
     """(B,N,Cp) -> (B,C,N)"""
     B, N, Cp = x_nc.shape
@@ -94,6 +121,7 @@ def to_channel_major(x_nc, C):
     return out
 
 
+@_on_device
 def group_points(points, idx):
     require_cuda(points, "points", F32)
     require_cuda(idx, "idx", I32)
@@ -105,6 +133,7 @@ def group_points(points, idx):
     return out
 
 
+@_on_device
 def group_points_grad(grad_out, idx, n):
     require_cuda(grad_out, "grad_out", F32)
     require_cuda(idx, "idx", I32)
@@ -115,6 +144,7 @@ def group_points_grad(grad_out, idx, n):
     return out
 
 
+@_on_device
 def reduce_partials(partial):
     """(T,P) -> (P,)"""
     T, P = partial.shape
@@ -130,6 +160,7 @@ FAM_POSPOOL_XYZ, FAM_POSPOOL_SINCOS, FAM_ADAPTIVE_DP, FAM_PSEUDOGRID = 0, 1, 2, 
 REDUCE = {"avg": 0, "mean": 0, "sum": 1, "max": 2}
 
 
+@_on_device
 def agg_fwd(family, reduction, feat_pm, query_xyz, support_xyz, idx, ncount, p0, p1, C, radius, normalize, shared=1,
             nkp=0, extent=1.0, influence=0, want_bn_partial=True):
     """-> (agg (B,C,M), bn_partial (ntiles,2,C) | None)"""
@@ -145,6 +176,7 @@ def agg_fwd(family, reduction, feat_pm, query_xyz, support_xyz, idx, ncount, p0,
     return agg, partial
 
 
+@_on_device
 def agg_bwd(family, reduction, g_pm, feat_pm, query_xyz, support_xyz, ncount, csr_off, csr_ent, p0, p1, C, N, K,
             radius, normalize, shared=1, nkp=0, extent=1.0, influence=0):
     """-> (grad_feat (B,C,N), param_grad (P//C, C) | None)   P = 4C (adaptive: x,y,z,bias) or nkp*C"""
@@ -164,6 +196,7 @@ def agg_bwd(family, reduction, g_pm, feat_pm, query_xyz, support_xyz, ncount, cs
     return grad_feat, pg
 
 
+@_on_device
 def bn_finalize(bn_partial, C, count, eps, momentum, training, running_mean, running_var):
     """-> save_stats (2,C): mean, invstd.  Updates running stats in place when training."""
     dev = running_mean.device if running_mean is not None else bn_partial.device
@@ -175,6 +208,7 @@ def bn_finalize(bn_partial, C, count, eps, momentum, training, running_mean, run
     return stats
 
 
+@_on_device
 def bn_relu_fwd(x, stats, gamma, beta):
     B, C, M = x.shape
     y = torch.empty_like(x)
@@ -183,6 +217,7 @@ def bn_relu_fwd(x, stats, gamma, beta):
     return y
 
 
+@_on_device
 def bn_relu_bwd(grad_y, x, stats, gamma, beta, training):
     """-> (g_pm (B,M,Cp) point-major d/d(agg), dgamma (C,), dbeta (C,))"""
     B, C, M = x.shape
@@ -202,6 +237,7 @@ def bn_relu_bwd(grad_y, x, stats, gamma, beta, training):
 GEMM_AUTO, GEMM_FFMA, GEMM_TC3X = 0, 1, 2
 
 
+@_on_device
 def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1, algo=GEMM_AUTO):
     """out[m][n] = sum_k a[m*sa_m + k*sa_k] * b[k*sb_k + n*sb_n]  (element strides; fp32 accuracy: 3xTF32 on
     the tcgen05 tensor cores, or the fp32 FMA kernel -- see cl3d.h)"""
@@ -217,6 +253,7 @@ def sgemm(a, sa_m, sa_k, b, sb_k, sb_n, M, N, K, out=None, ldc=None, splitk=1, a
     return out
 
 
+@_on_device
 def to_point_major_aug(x_cn, xyz, radius):
     """(B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | xyz/r | 0], Cpa = padded(C+3)"""
     require_cuda(x_cn, "features", F32)
@@ -227,6 +264,7 @@ def to_point_major_aug(x_cn, xyz, radius):
     return out
 
 
+@_on_device
 def pwmlp_prep_weights(conv_weight, gamma, C, Cout):
     """-> wcat (2Cop, Cpa) rows zero-padded to Cpa = padded(C+3), wp (Cout,3), sgn (Cout)"""
     dev = conv_weight.device
@@ -239,6 +277,7 @@ def pwmlp_prep_weights(conv_weight, gamma, C, Cout):
     return wcat, wp, sgn
 
 
+@_on_device
 def pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout):
     gW = torch.empty(Cout, 3 + 2 * C, 1, 1, dtype=F32, device=gwcat.device)
     check(_lib.lib().cl3d_pwmlp_weight_grad(ptr(gwcat), ptr(grad_wp), ptr(sgn), C, Cout, ptr(gW), stream_ptr()),
@@ -246,7 +285,8 @@ def pwmlp_weight_grad(gwcat, grad_wp, sgn, C, Cout):
     return gW
 
 
-def pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, idx, Cout, radius):
+@_on_device
+def pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, support_xyz, idx, Cout, radius):
     B, N, _ = ab_pm.shape
     M, K = idx.shape[1], idx.shape[2]
     L = _lib.lib()
@@ -257,12 +297,13 @@ def pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, idx, Cout, radius):
     sq = torch.empty(B, M, Cop, dtype=F32, device=dev)
     karg = torch.empty(B, M, Cop, dtype=torch.uint8, device=dev)
     partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, Cout, dtype=F32, device=dev)
-    check(L.cl3d_pwmlp_fwd_stats(ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(idx), B, N, M, K, Cout,
+    check(L.cl3d_pwmlp_fwd_stats(ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(support_xyz), ptr(idx), B, N, M, K, Cout,
                                  float(radius), ptr(ysel), ptr(aq), ptr(sq), ptr(karg), ptr(partial), stream_ptr()),
           "cl3d_pwmlp_fwd_stats")
     return ysel, aq, sq, karg, partial
 
 
+@_on_device
 def pwmlp_fwd_out(ysel, stats, gamma, beta):
     B, Cout, M = ysel.shape
     out = torch.empty_like(ysel)
@@ -271,8 +312,9 @@ def pwmlp_fwd_out(ysel, stats, gamma, beta):
     return out
 
 
-def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, ysel, aq, sq, karg, stats, gamma,
-              radius, side_stream=None):
+@_on_device
+def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, support_xyz, idx, csr_off, csr_ent, ysel, aq, sq, karg, stats, gamma,
+              radius, side_stream=None, training=True):
     """-> (grad_ab_pm (B,N,2Cop), grad_wp (3,Cout), dgamma (Cout), dbeta (Cout)); side_stream: a torch stream the
     library may fork onto (zero-fill + query pass run beside the gather pass), joined before it returns"""
     B, N, C2 = ab_pm.shape
@@ -283,9 +325,10 @@ def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, y
     dgb = torch.empty(2, Cout, dtype=F32, device=dev)
     grad_ab = torch.empty(B, N, C2, dtype=F32, device=dev)
     grad_wp = torch.empty(3, Cout, dtype=F32, device=dev)
-    check(L.cl3d_pwmlp_bwd(ptr(grad_out), ptr(out), ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(idx),
+    check(L.cl3d_pwmlp_bwd(ptr(grad_out), ptr(out), ptr(ab_pm), ptr(wp), ptr(sgn), ptr(query_xyz), ptr(support_xyz), ptr(idx),
                            ptr(csr_off), ptr(csr_ent), ptr(ysel), ptr(aq), ptr(sq), ptr(karg), ptr(stats), ptr(gamma),
-                           B, N, M, K, Cout, float(radius), ptr(partial), ptr(dgb), ptr(grad_ab), ptr(grad_wp),
+                           B, N, M, K, Cout, float(radius), int(bool(training)), ptr(partial), ptr(dgb), ptr(grad_ab),
+                           ptr(grad_wp),
                            stream_ptr(), ctypes.c_void_p(side_stream.cuda_stream) if side_stream is not None else None),
           "cl3d_pwmlp_bwd")
     return grad_ab, grad_wp, dgb[0], dgb[1]
@@ -294,6 +337,7 @@ def pwmlp_bwd(grad_out, out, ab_pm, wp, sgn, query_xyz, idx, csr_off, csr_ent, y
 # --------------------------------------------------------------------------------------------------
 # grid subsampling, fused max-pool
 # --------------------------------------------------------------------------------------------------
+@_on_device
 def grid_subsample(points, mask, npoint, sampleDl):
     """-> (sub_xyz (B,m,3) f32, sub_mask (B,m) i32); bit-exact with masked_grid_subsampling_gpu.cu:11-153"""
     require_cuda(points, "points", F32)
@@ -311,6 +355,7 @@ def grid_subsample(points, mask, npoint, sampleDl):
     return sub, sm
 
 
+@_on_device
 def gather_max(features, idx):
     """out[b,c,q] = max_k features[b,c,idx[b,q,k]] -> (out (B,C,M), arg (B,M,Cp) uint8)"""
     require_cuda(features, "features", F32)
@@ -325,6 +370,7 @@ def gather_max(features, idx):
     return out, arg
 
 
+@_on_device
 def gather_max_grad(grad_out, idx, arg, N):
     B, C, M = grad_out.shape
     K = idx.shape[2]

@@ -27,10 +27,10 @@ class _FusedPointWiseMLP(Function):
         # AB[p][n] = sum_c fa[p][c] * wcat[n][c]   (both row-padded to Cpa with zeros -> k runs over Cpa)
         ab_pm = ops.sgemm(fa_pm, Cpa, 1, wcat, 1, Cpa, B * N, 2 * Cop, Cpa).view(B, N, 2 * Cop)
         nl.wait()                                   # the search ran on the side stream, overlapping the product
-        if any(ctx.needs_input_grad):
-            nl.prefetch_csr(all_slots=True)         # lists for the backward, built behind the forward kernels
-        ysel, aq, sq, karg, partial = ops.pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, nl.idx, Cout, radius)
         training = bn.training or (bn.running_mean is None)
+        if any(ctx.needs_input_grad) and training:
+            nl.prefetch_csr(all_slots=True)         # lists for the backward, built behind the forward kernels
+        ysel, aq, sq, karg, partial = ops.pwmlp_fwd_stats(ab_pm, wp, sgn, query_xyz, support_xyz, nl.idx, Cout, radius)
         momentum = bn.momentum if bn.momentum is not None else 0.0
         if training and bn.running_mean is not None:
             bn.num_batches_tracked.add_(1)
@@ -40,21 +40,22 @@ class _FusedPointWiseMLP(Function):
                                 bn.running_var)
         out = ops.pwmlp_fwd_out(ysel, stats, bn_weight, bn_bias)
         ctx.nl, ctx.radius, ctx.training, ctx.dims = nl, radius, training, (B, C, N, M, K, Cout, Cop, Cpa)
-        ctx.save_for_backward(out, fa_pm, ab_pm, wp, sgn, wcat, ysel, aq, sq, karg, stats, bn_weight, query_xyz)
+        ctx.save_for_backward(out, fa_pm, ab_pm, wp, sgn, wcat, ysel, aq, sq, karg, stats, bn_weight, query_xyz,
+                              support_xyz)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        out, fa_pm, ab_pm, wp, sgn, wcat, ysel, aq, sq, karg, stats, bn_weight, query_xyz = ctx.saved_tensors
+        (out, fa_pm, ab_pm, wp, sgn, wcat, ysel, aq, sq, karg, stats, bn_weight, query_xyz,
+         support_xyz) = ctx.saved_tensors
         B, C, N, M, K, Cout, Cop, Cpa = ctx.dims
-        if not ctx.training:
-            raise NotImplementedError("PointWiseMLP backward in eval mode (running statistics) is not fused")
         nl = ctx.nl
-        off, ent = nl.csr_all_slots()
+        # eval mode (frozen BatchNorm): no batch-statistics terms -> no dense pass, no transposed lists needed
+        off, ent = nl.csr_all_slots() if ctx.training else (None, None)
         side = pt_utils._side_stream(out.device, priority=-1) if pt_utils.overlap_enabled else None
-        grad_ab, grad_wp, dgamma, dbeta = ops.pwmlp_bwd(grad_out.contiguous(), out, ab_pm, wp, sgn, query_xyz, nl.idx,
+        grad_ab, grad_wp, dgamma, dbeta = ops.pwmlp_bwd(grad_out.contiguous(), out, ab_pm, wp, sgn, query_xyz, support_xyz, nl.idx,
                                                         off, ent, ysel, aq, sq, karg, stats, bn_weight, ctx.radius,
-                                                        side_stream=side)
+                                                        side_stream=side, training=ctx.training)
         P = B * N
         Cp = ops.padded_channels(C)
         # the two products of the backward are independent: the weight gradient runs on the side stream

@@ -43,11 +43,19 @@ def install(reference_pytorch_root=None):
     if reference_pytorch_root:
         if reference_pytorch_root not in sys.path:
             sys.path.insert(0, reference_pytorch_root)
-        # `models` is the reference's package; its operator module is replaced by ours before resnet imports it
-        pkg = importlib.import_module("models") if os.path.isdir(os.path.join(reference_pytorch_root, "models")) else None
+        # The operator module must be replaced BEFORE the reference's `models` package is imported: models/__init__
+        # -> build -> backbones/resnet.py:3 runs `from ..local_aggregation_operators import LocalAggregation` during
+        # that import, and a name bound by a from-import is not re-bound by a later sys.modules change.
         sys.modules["models.local_aggregation_operators"] = lao
-        if pkg is not None:
+        if os.path.isdir(os.path.join(reference_pytorch_root, "models")):
+            pkg = importlib.import_module("models")
             pkg.local_aggregation_operators = lao
+            # a `models` package imported before install() already holds the reference's classes: re-bind them
+            for name, mod in list(sys.modules.items()):
+                if mod is not None and (name == "models" or name.startswith("models.")) and mod is not lao:
+                    for attr in ("LocalAggregation", "PosPool", "AdaptiveWeight", "PointWiseMLP", "PseudoGrid"):
+                        if hasattr(mod, attr) and getattr(mod, attr) is not getattr(lao, attr):
+                            setattr(mod, attr, getattr(lao, attr))
 
 
 def reference_config(yaml_path):

@@ -109,7 +109,8 @@ int cl3d_build_csr(const int* idx, const int* ncount, int B, int N, int M, int K
  * ---------------------------------------------------------------------------------------------- */
 int cl3d_group_points(const float* points /*(B,C,N)*/, const int* idx /*(B,M,K)*/, int B, int C, int N,
                       int M, int K, float* out /*(B,C,M,K)*/, cl3d_stream_t stream);
-/* grad_points (B,C,N) is fully overwritten (zero-filled first), deterministic summation order. */
+/* grad_points (B,C,N) is fully overwritten (zero-filled first); contributions are added with fp32 atomics, so the
+ * summation order -- like the reference's group_points_grad_gpu.cu:48-69 -- is not deterministic (tolerance parity). */
 int cl3d_group_points_grad(const float* grad_out /*(B,C,M,K)*/, const int* idx, int B, int C, int N,
                            int M, int K, float* grad_points, cl3d_stream_t stream);
 
@@ -216,7 +217,8 @@ int cl3d_sgemm_algo(const float* a, long long sa_m, long long sa_k, const float*
                     size_t workspace_bytes, int algo, cl3d_stream_t stream);
 
 /* Fused PointWiseMLP (pwmlp.cu).  Cop = cl3d_padded_channels(Cout), Cpa = cl3d_padded_channels(C+3).
- *   cl3d_to_point_major_aug : (B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | xyz/r | 0]
+ *   cl3d_to_point_major_aug : (B,C,N) features + (B,N,3) xyz -> (B,N,Cpa) rows [f | (xyz - o_b)/r | 0], o_b = xyz[b,0]
+ *                             (support_xyz of fwd_stats / bwd supplies the same origin for the query term)
  *   ab_pm (B,N,2*Cop)       : row = [A | T],  A = (Wc-Wr) f,  T = sgn*(Wr f + Wp s/r)   (one cl3d_sgemm)
  *   wp (Cout,3), sgn (Cout) : conv weight columns 0..2; sign(gamma) as +-1.0
  * fwd_stats : ysel (B,Cout,M) selected extremum of y; aq, sq (B,M,Cop) a' and sum_k bv; karg (B,M,Cop) uint8
@@ -229,7 +231,8 @@ int cl3d_sgemm_algo(const float* a, long long sa_m, long long sa_k, const float*
  *             red.add); side_stream (may be NULL): the zero-fill and the query pass run on it beside the other
  *             two passes, forked from and joined back into `stream` with events (CUDA-graph capturable);
  *             grad_wp (3,Cout) = the -sum da' (x) q/r part of d/dWp (the rest comes out of the weight-gradient
- *             product). */
+ *             product).  training = 0: BatchNorm2d in eval mode (save_stats = running statistics): its backward
+ *             has no batch-statistics terms, dy = sc*dz at the arg-max slot only (csr lists may then be NULL). */
 size_t cl3d_pwmlp_bwd_scratch_floats(int B, int N, int M, int Cout);
 /* conv weight (Cout, 3+2C) = [Wp|Wc|Wr] + BN gamma -> wcat (2*Cop, Cpa) (rows zero-padded to Cpa), wp (Cout,3),
  * sgn (Cout); and back: d/dwcat (2*Cop, Cpa) + grad_wp (3,Cout) -> d/d(conv weight) (Cout, 3+2C). */
@@ -240,15 +243,16 @@ int cl3d_pwmlp_weight_grad(const float* gwcat, const float* grad_wp, const float
 int cl3d_to_point_major_aug(const float* in_cn, const float* xyz, int B, int C, int N, float radius,
                             float* out_nc, cl3d_stream_t stream);
 int cl3d_pwmlp_fwd_stats(const float* ab_pm, const float* wp, const float* sgn, const float* query_xyz,
-                         const int* idx, int B, int N, int M, int K, int Cout, float radius, float* ysel,
+                         const float* support_xyz, const int* idx, int B, int N, int M, int K, int Cout,
+                         float radius, float* ysel,
                          float* aq, float* sq, unsigned char* karg, float* bn_partial, cl3d_stream_t stream);
 int cl3d_pwmlp_fwd_out(const float* ysel, const float* save_stats, const float* gamma, const float* beta,
                        int B, int M, int Cout, float* out, cl3d_stream_t stream);
 int cl3d_pwmlp_bwd(const float* grad_out, const float* out, const float* ab_pm, const float* wp,
-                   const float* sgn, const float* query_xyz, const int* idx, const int* csr_off,
-                   const int* csr_ent, const float* ysel, const float* aq, const float* sq,
+                   const float* sgn, const float* query_xyz, const float* support_xyz, const int* idx,
+                   const int* csr_off, const int* csr_ent, const float* ysel, const float* aq, const float* sq,
                    const unsigned char* karg, const float* save_stats, const float* gamma, int B, int N,
-                   int M, int K, int Cout, float radius, float* scratch, float* dgamma_dbeta,
+                   int M, int K, int Cout, float radius, int training, float* scratch, float* dgamma_dbeta,
                    float* grad_ab_pm, float* grad_wp, cl3d_stream_t stream, cl3d_stream_t side_stream);
 
 #ifdef __cplusplus

@@ -100,10 +100,16 @@ from models.backbones.resnet import ResNet
 import closerlook3d_b200.local_aggregation_operators as mine
 import models.local_aggregation_operators as theirs
 assert theirs.LocalAggregation is mine.LocalAggregation
+import models.backbones.resnet as rn
+assert rn.LocalAggregation is mine.LocalAggregation, "resnet bound the reference's unfused LocalAggregation"
+import pt_utils as ptu, closerlook3d_b200.pt_utils as mine_ptu
+assert ptu is mine_ptu and rn.MaskedMaxPool is mine_ptu.MaskedMaxPool
 cfg = shim.reference_config("/root/reference/pytorch/cfgs/s3dis/pospool_xyz_avg.yaml")
 net = ResNet(cfg, cfg.input_features_dim, cfg.radius, cfg.sampleDl, cfg.nsamples, cfg.npoints, width=cfg.width, depth=cfg.depth, bottleneck_ratio=cfg.bottleneck_ratio)
 n = sum(p.numel() for p in net.parameters())
 assert n > 1e6, n
+las = [m for m in net.modules() if type(m).__name__ == "LocalAggregation"]
+assert las and all(type(m) is mine.LocalAggregation for m in las), "backbone holds foreign LocalAggregation modules"
 print("params", n)
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
@@ -147,8 +153,22 @@ def _gloo_worker(rank, world, port, q):
     x = torch.arange(40, dtype=torch.float32).view(10, 4)[lo:hi]
     w(x).sum().backward()
     cdist.allreduce_gradients(list(w.parameters()), average=False)
+    g_copy = (w.weight.grad.tolist(), w.bias.grad.tolist())
+    # the same exchange through the persistent flat buffer (p.grad are views: one collective, nothing copied)
+    w2 = torch.nn.Linear(4, 3)
+    w2.load_state_dict(w.state_dict())
+    fg = cdist.FlatGradients(list(w2.parameters())).attach()
+    fg.zero()
+    w2(x).sum().backward()
+    assert w2.weight.grad.data_ptr() == fg.flat.data_ptr()          # autograd accumulated in place
+    cdist.allreduce_gradients(list(w2.parameters()), average=False)  # takes the no-copy path
+    assert w2.weight.grad.tolist() == g_copy[0] and w2.bias.grad.tolist() == g_copy[1]
+    fg.zero()
+    w2(x).sum().backward()
+    fg.allreduce(average=True)
+    assert torch.allclose(w2.weight.grad * world, torch.tensor(g_copy[0]))
     # plain lists: a tensor would travel as a shared-memory handle that dies with this process
-    q.put((rank, lo, hi, w.weight.grad.tolist(), w.bias.grad.tolist()))
+    q.put((rank, lo, hi, g_copy[0], g_copy[1]))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -37,7 +37,10 @@ def _randomize_bn(module, seed):
 
 
 def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=None, train=True, tol=TOL,
-             param_tol=PARAM_TOL):
+             param_tol=PARAM_TOL, oracle_device="cpu", offset=0.0):
+    """oracle_device="cpu": la_oracle over the C restatement (oracle/cl3d_oracle.c) on the host;
+    oracle_device=cuda: la_oracle over `oracle_ext` = the reference's OWN CUDA extension (oracle/_ref) on the GPU,
+    i.e. the reference's GPU path itself (TF32 off) -- used at the full BASELINE sizes."""
     from closerlook3d_b200.local_aggregation_operators import LocalAggregation
     from oracle import la_oracle
     cfg = la_config(la_type, **over)
@@ -50,6 +53,8 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     sd = copy.deepcopy(mod.state_dict())
     d = synth.make_cloud_batch(B, N, C, seed)
     xyz, mask, feats = d["xyz"], d["mask"], d["features"]
+    if offset:
+        xyz = (xyz + offset).contiguous()   # a scene far from the coordinate origin
     if M is None:
         q, qm = xyz, mask
     else:  # strided block: queries are a different (smaller) set near the supports
@@ -60,13 +65,19 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     gout = torch.randn(B, C, q.shape[1], generator=torch.Generator().manual_seed(seed + 2))
 
     # ---- forward on both sides (the oracle follows the reference's GPU arithmetic for `/= radius`, see la_oracle)
-    la_oracle.GPU_SCALAR_DIVISION = True
-    la_oracle.DIM_MAT_FN = lambda fd: torch.pow(
-        1.0 * 1000, (1.0 / fd) * torch.arange(fd, dtype=torch.float32).to(cuda)).cpu()   # reference :72-75 on its device
-    orc = la_oracle.OracleLocalAggregation(oracle_ext, la_type, C, C, r, K, cfg, sd)
+    on_gpu = str(oracle_device) != "cpu"
+    if on_gpu:   # the reference's arithmetic on its own device: nothing to emulate
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    else:
+        la_oracle.GPU_SCALAR_DIVISION = True
+        la_oracle.DIM_MAT_FN = lambda fd: torch.pow(
+            1.0 * 1000, (1.0 / fd) * torch.arange(fd, dtype=torch.float32).to(cuda)).cpu()   # reference :72-75 on its device
+    orc = la_oracle.OracleLocalAggregation(oracle_ext, la_type, C, C, r, K, cfg, sd, device=oracle_device)
     orc.training = train
-    f_ref = feats.clone().requires_grad_(True)
-    o_ref = orc(q, xyz, qm, mask, f_ref)
+    od = oracle_device
+    f_ref = feats.clone().to(od).requires_grad_(True)
+    o_ref = orc(q.to(od), xyz.to(od), qm.to(od), mask.to(od), f_ref)
     mod = mod.to(cuda)
     mod.train(train)
     f = feats.to(cuda).requires_grad_(True)
@@ -76,29 +87,29 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     # per million) get zero upstream gradient on BOTH sides, so the comparison is well-posed.
     la_oracle.GPU_SCALAR_DIVISION = False
     la_oracle.DIM_MAT_FN = None
-    flips = (out.detach().cpu() > 0) != (o_ref.detach() > 0)
+    flips = (out.detach().cpu() > 0) != (o_ref.detach().cpu() > 0)
     assert int(flips.sum()) <= max(2, out.numel() // 100000), f"{int(flips.sum())} ReLU sign flips"
     gout = gout * (~flips)
-    (o_ref * gout).sum().backward()
+    (o_ref * gout.to(od)).sum().backward()
     (out * gout.to(cuda)).sum().backward()
     torch.cuda.synchronize()
 
     assert out.shape == o_ref.shape
     assert not torch.isnan(out).any()
-    e_out = _rel_err(out.detach().cpu(), o_ref.detach())
-    e_gf = _rel_err(f.grad.cpu(), f_ref.grad)
+    e_out = _rel_err(out.detach().cpu(), o_ref.detach().cpu())
+    e_gf = _rel_err(f.grad.cpu(), f_ref.grad.cpu())
     assert e_out <= tol, f"output err {e_out}"
     assert e_gf <= tol, f"grad_features err {e_gf}"
     ref_grads = orc.grads()
     for name, p in mod.named_parameters():
         k = name[len("local_aggregation_operator."):]
         assert p.grad is not None, f"no grad for {name}"
-        e = _rel_err(p.grad.cpu(), ref_grads[k])
+        e = _rel_err(p.grad.cpu(), ref_grads[k].cpu())
         assert e <= param_tol, f"grad {name} err {e}"
     sd2 = mod.state_dict()
     for k, v in orc.st.items():
         if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
-            e = _rel_err(sd2["local_aggregation_operator." + k].float().cpu(), v.float())
+            e = _rel_err(sd2["local_aggregation_operator." + k].float().cpu(), v.float().cpu())
             assert e <= tol, f"buffer {k} err {e}"
     return e_out, e_gf
 
@@ -137,13 +148,23 @@ def test_family_matches_oracle(cuda, oracle_ext, la_type, over, B, N, K, C):
 
 @pytest.mark.parametrize("la_type,over", [("pospool", XYZ_AVG), ("adaptive_weight", AW), ("pseudo_grid", dict()),
                                           ("pointwisemlp", PW)])
+def test_scene_far_from_origin(cuda, oracle_ext, la_type, over):
+    # S3DIS-like coordinates: |xyz| / radius ~ 150.  The relative positions are differences of nearby points, so the
+    # result must not lose accuracy (PointWiseMLP's separable per-point / per-query terms are centred per cloud).
+    run_case(cuda, oracle_ext, la_type, over, 2, 1024, 16, 72, seed=91, offset=25.0)
+
+
+@pytest.mark.parametrize("la_type,over", [("pospool", XYZ_AVG), ("adaptive_weight", AW), ("pseudo_grid", dict()),
+                                          ("pointwisemlp", PW)])
 def test_strided_queries(cuda, oracle_ext, la_type, over):
     # queries != supports (strided bottleneck): M < N, padded queries, some queries with few neighbours
     run_case(cuda, oracle_ext, la_type, over, 3, 2400, 16, 72, seed=31, M=600, radius=0.15)
 
 
-@pytest.mark.parametrize("la_type,over", [("pospool", XYZ_AVG), ("pseudo_grid", dict())])
+@pytest.mark.parametrize("la_type,over", [("pospool", XYZ_AVG), ("pseudo_grid", dict()), ("adaptive_weight", AW),
+                                          ("pospool", SINCOS_AVG), ("pointwisemlp", PW)])
 def test_eval_mode_uses_running_stats(cuda, oracle_ext, la_type, over):
+    # forward with running statistics AND the backward through the frozen BatchNorm (fine-tuning with frozen BN)
     run_case(cuda, oracle_ext, la_type, over, 2, 1024, 16, 72, seed=77, train=False)
 
 
