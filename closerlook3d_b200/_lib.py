@@ -26,6 +26,8 @@ SIGNATURES = {
     "cl3d_ball_query_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cl3d_ball_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cl3d_ball_query_algo": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "cl3d_ball_query_csr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "cl3d_ball_query_csr": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "cl3d_nearest_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "cl3d_csr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cl3d_build_csr": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -107,7 +109,7 @@ def _wrap(name, fn):
 
 
 _UNTIMED = {"cl3d_version", "cl3d_last_error", "cl3d_padded_channels", "cl3d_sm_count", "cl3d_launch_count",
-            "cl3d_ball_query_workspace_bytes", "cl3d_csr_workspace_bytes", "cl3d_grid_subsample_workspace_bytes",
+            "cl3d_ball_query_workspace_bytes", "cl3d_ball_query_csr_workspace_bytes", "cl3d_csr_workspace_bytes", "cl3d_grid_subsample_workspace_bytes",
             "cl3d_agg_num_tiles", "cl3d_agg_bwd_num_blocks", "cl3d_agg_num_params", "cl3d_sgemm_workspace_bytes", "cl3d_pwmlp_bwd_scratch_floats"}
 
 

@@ -18,6 +18,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC"]
 
 
+EXTRA_FLAGS = {}  # per-file additions to NVCC_FLAGS, e.g. {"x.cu": ["-fmad=false"]}
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -45,7 +48,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ_DIR, s[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
-            cmds.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
+            cmds.append([nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(s, []) + ["-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:

@@ -22,34 +22,9 @@
 // r1a staged the rows with one cp.async.bulk (TMA) per row; ncu showed that design issue-bound (UBLKCP is a
 // uniform instruction: ~11 warp-instructions per 288-byte row, plus the LDS to read it back), 3-5x slower than
 // this version.  See profiles/r1a_pwmlp_fwd_tma_summary.md.
-#include "common.cuh"
+#include "agg_common.cuh"
 
 namespace cl3d {
-
-constexpr int kAggWarps = 8;
-constexpr int kTile = 32;   // queries (fwd) / support points (bwd) per CTA tile
-constexpr int kMaxKP = 16;  // PseudoGrid kernel points (reference default 15)
-constexpr int kMaxCI = 6;   // channel chunk = 32*CI <= 192 channels per CTA
-constexpr int kSlots = 32;  // neighbour slots (fwd) / CSR entries (bwd) staged per round
-
-struct AggArgs {
-  const float* feat_pm;      // (B,N,Cp)   fwd: features; bwd: features (for parameter gradients)
-  const float* g_pm;         // (B,M,Cp)   bwd only
-  const float* query_xyz;    // (B,M,3)
-  const float* support_xyz;  // (B,N,3)
-  const int* idx;            // (B,M,K)    fwd only
-  const int* ncount;         // (B,M)
-  const int* csr_off;        // (B,N+1)    bwd only
-  const int* csr_ent;        // (B,M*K)    bwd only
-  const float* p0;           // family parameter 0 (see cl3d.h)
-  const float* p1;           // family parameter 1
-  float* out;                // fwd: agg (B,C,M); bwd: grad_feat (B,C,N)
-  float* partial;            // fwd: bn partial (ntiles,2,C); bwd: param-grad partial (gridDim.x, P)
-  int B, N, M, K, C, Cp;
-  int reduction, normalize, shared, nkp, influence;
-  float inv_radius, extent, inv_extent;
-  int ntiles;
-};
 
 // ---------------------------------------------------------------------------------------------
 // family weights
@@ -653,38 +628,86 @@ __device__ __forceinline__ float div_by(float n, float d, float rcp_d) {
   return q;
 }
 
+// Two arguments at once (the same wave length for two neighbour slots), all arithmetic packed fp32x2: the same
+// Cody-Waite reduction and polynomials as sincos_small, with the nearest integer taken by the magic-number add
+// (t = x * 2/pi + 1.5 * 2^23: the integer sits in the low mantissa bits, so no F2I / FRND on the slow pipe) and the
+// sin and cos polynomials evaluated side by side.  7 FMA-pipe instructions per (neighbour, wave length) instead of 25.
+__device__ __forceinline__ void sincos_small2(u64 x2, u64& sn2, u64& cs2) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23
+  const u64 t2 = fma2(x2, pack2(0.636619747f, 0.636619747f), pack2(kMagic, kMagic));
+  const u64 j2 = sub2(t2, pack2(kMagic, kMagic));
+  u64 r2v = fma2(j2, pack2(-1.57079601e+00f, -1.57079601e+00f), x2);
+  r2v = fma2(j2, pack2(-3.13916473e-07f, -3.13916473e-07f), r2v);
+  r2v = fma2(j2, pack2(-5.39030253e-15f, -5.39030253e-15f), r2v);
+  const u64 rr = mul2(r2v, r2v);
+  u64 ps = fma2(rr, pack2(-1.95152959e-4f, -1.95152959e-4f), pack2(8.33216087e-3f, 8.33216087e-3f));
+  ps = fma2(ps, rr, pack2(-1.66666546e-1f, -1.66666546e-1f));
+  ps = fma2(mul2(ps, rr), r2v, r2v);                                           // sin(r)
+  u64 pc = fma2(rr, pack2(2.44331571e-5f, 2.44331571e-5f), pack2(-1.38873163e-3f, -1.38873163e-3f));
+  pc = fma2(pc, rr, pack2(4.16666457e-2f, 4.16666457e-2f));
+  pc = fma2(pc, rr, pack2(-0.5f, -0.5f));
+  pc = fma2(pc, rr, pack2(1.0f, 1.0f));                                        // cos(r)
+  float ta, tb, sa, sb, ca, cb;
+  unpack2(t2, ta, tb);
+  unpack2(ps, sa, sb);
+  unpack2(pc, ca, cb);
+  const unsigned qa = __float_as_uint(ta), qb = __float_as_uint(tb);            // quadrant = low two bits
+  const float s0a = (qa & 1u) ? ca : sa, c0a = (qa & 1u) ? sa : ca;
+  const float s0b = (qb & 1u) ? cb : sb, c0b = (qb & 1u) ? sb : cb;
+  sn2 = pack2(__uint_as_float(__float_as_uint(s0a) ^ ((qa << 30) & 0x80000000u)),
+              __uint_as_float(__float_as_uint(s0b) ^ ((qb << 30) & 0x80000000u)));
+  cs2 = pack2(__uint_as_float(__float_as_uint(c0a) ^ (((qa + 1u) << 30) & 0x80000000u)),
+              __uint_as_float(__float_as_uint(c0b) ^ (((qb + 1u) << 30) & 0x80000000u)));
+}
+
 template <int PI, bool BWD>
 __device__ __forceinline__ void consume_pairs(const float* __restrict__ base, const float4* __restrict__ s_dp,
                                               const float* __restrict__ s_h, int n, const PairLane<PI>& pl,
                                               float (&as)[PI], float (&ac)[PI]) {
-  constexpr int U = 2;
+  // neighbour slots two at a time: component 0 = even slot, component 1 = odd slot of the pair; each half keeps its
+  // own partial sum (added at the end), every operation is a packed IEEE operation on both slots
+  u64 as2[PI], ac2[PI], nd2[PI], rd2[PI];
+#pragma unroll
+  for (int i = 0; i < PI; ++i) {
+    as2[i] = ac2[i] = 0ull;
+    nd2[i] = pack2(-pl.dim[i], -pl.dim[i]);
+    rd2[i] = pack2(pl.rdim[i], pl.rdim[i]);
+  }
+  const u64 hundred = pack2(100.f, 100.f);
   int s = 0;
-  for (; s + U <= n; s += U) {
-    float4 dp[U];
-    float vs[U][PI], vc[U][PI];
+  for (; s + 2 <= n; s += 2) {
+    const float4 dp0 = s_dp[s], dp1 = s_dp[s + 1];
+    const unsigned o0 = __float_as_uint(dp0.w), o1 = __float_as_uint(dp1.w);   // row element offsets
+    u64 vs2[PI], vc2[PI];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      dp[u] = s_dp[s + u];
-      const float* row = base + __float_as_uint(dp[u].w);
-#pragma unroll
-      for (int i = 0; i < PI; ++i) {
-        vs[u][i] = __ldg(row + pl.osin[i]);
-        vc[u][i] = __ldg(row + pl.ocos[i]);
-      }
+    for (int i = 0; i < PI; ++i) {  // one 32-bit add + one IMAD.WIDE per address (row_at)
+      vs2[i] = pack2(__ldg(row_at(base, o0 + pl.osin[i])), __ldg(row_at(base, o1 + pl.osin[i])));
+      vc2[i] = pack2(__ldg(row_at(base, o0 + pl.ocos[i])), __ldg(row_at(base, o1 + pl.ocos[i])));
     }
+    u64 sc2 = 0ull;
+    if constexpr (BWD) sc2 = pack2(s_h[s], s_h[s + 1]);
+    const u64 px = mul2(pack2(dp0.x, dp1.x), hundred), py = mul2(pack2(dp0.y, dp1.y), hundred),
+              pz = mul2(pack2(dp0.z, dp1.z), hundred);   // alpha * dp  (:75)
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float sc = BWD ? s_h[s + u] : 1.f;
-#pragma unroll
-      for (int i = 0; i < PI; ++i) {
-        const float pcomp = pl.axis[i] == 0 ? dp[u].x : (pl.axis[i] == 1 ? dp[u].y : dp[u].z);
-        const float arg = div_by(__fmul_rn(100.f, pcomp), pl.dim[i], pl.rdim[i]);  // torch.div(alpha*dp, dim_mat)
-        float sn, cs;
-        sincos_small(arg, sn, cs);
-        as[i] = fmaf(BWD ? vs[u][i] * sc : vs[u][i], sn, as[i]);
-        ac[i] = fmaf(BWD ? vc[u][i] * sc : vc[u][i], cs, ac[i]);
-      }
+    for (int i = 0; i < PI; ++i) {
+      const u64 n2 = pl.axis[i] == 0 ? px : (pl.axis[i] == 1 ? py : pz);
+      // torch.div(alpha * dp, dim_mat): correctly rounded quotient, two Markstein corrections (see div_by)
+      u64 q2 = mul2(n2, rd2[i]);
+      q2 = fma2(fma2(nd2[i], q2, n2), rd2[i], q2);
+      q2 = fma2(fma2(nd2[i], q2, n2), rd2[i], q2);
+      u64 sn2, cs2;
+      sincos_small2(q2, sn2, cs2);
+      as2[i] = fma2(BWD ? mul2(vs2[i], sc2) : vs2[i], sn2, as2[i]);
+      ac2[i] = fma2(BWD ? mul2(vc2[i], sc2) : vc2[i], cs2, ac2[i]);
     }
+  }
+#pragma unroll
+  for (int i = 0; i < PI; ++i) {
+    float a0, a1, c0, c1;
+    unpack2(as2[i], a0, a1);
+    unpack2(ac2[i], c0, c1);
+    as[i] += a0 + a1;
+    ac[i] += c0 + c1;
   }
   for (; s < n; ++s) {
     const float4 dp = s_dp[s];
@@ -1019,6 +1042,7 @@ extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, con
   a.partial = bn_partial;
   fill_common(a, B, N, M, K, C, radius, reduction, normalize, shared, nkp, extent, influence);
   a.ntiles = B * ceil_div(M, kTile);
+  if (family == CL3D_FAM_PSEUDOGRID && pg2_supported(a)) return pg2_launch_fwd(a, (cudaStream_t)stream_);
   return dispatch_fwd(family, pick_ci(family, a.Cp), a, (cudaStream_t)stream_);
 }
 
@@ -1048,5 +1072,7 @@ extern "C" int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const 
   a.partial = grad_params_partial;
   fill_common(a, B, N, M, K, C, radius, reduction, normalize, shared, nkp, extent, influence);
   a.ntiles = B * ceil_div(N, kTile);
+  if (family == CL3D_FAM_PSEUDOGRID && pg2_supported(a))
+    return pg2_launch_bwd(a, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);
   return dispatch_bwd(family, pick_ci(family, a.Cp), a, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);
 }

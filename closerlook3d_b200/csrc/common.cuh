@@ -99,6 +99,73 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell: FFMA2 / FMUL2 / FADD2).  A register-operand FFMA issues every other
+// cycle per scheduler; the packed forms carry two IEEE operations in the same slot.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {  // a - b, component-wise (exactly rounded like __fsub_rn)
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU: 2^-22 relative, sqrt(0) = 0
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ u64 fma2_bcast(float h, u64 b, u64 c) {  // (h, h) * b + c ; h is a scalar-broadcast operand
+  u64 d;
+  asm("{\n.reg .b64 hh;\nmov.b64 hh, {%1, %1};\nfma.rn.f32x2 %0, hh, %2, %3;\n}" : "=l"(d) : "f"(h), "l"(b), "l"(c));
+  return d;
+}
+
+// The same operations on plain float operands (32-bit "f" constraints).  ptxas then allocates the register pairs
+// itself and keeps loop-carried accumulators in place; with 64-bit "l" operands it computed into the freshly loaded
+// pair and copied the result back with four MOVs per step (profiles/r2e).
+//   (cx, cy) += (h, h) * (bx, by)
+__device__ __forceinline__ void ffma2_bcast(float h, float bx, float by, float& cx, float& cy) {
+  asm("{\n.reg .b64 a, b, hh;\nmov.b64 a, {%0, %1};\nmov.b64 b, {%3, %4};\nmov.b64 hh, {%2, %2};\n"
+      "fma.rn.f32x2 a, hh, b, a;\nmov.b64 {%0, %1}, a;\n}"
+      : "+f"(cx), "+f"(cy)
+      : "f"(h), "f"(bx), "f"(by));
+}
+//   (cx, cy) += (ax, ay) * (bx, by)
+__device__ __forceinline__ void ffma2(float ax, float ay, float bx, float by, float& cx, float& cy) {
+  asm("{\n.reg .b64 a, b, c;\nmov.b64 a, {%2, %3};\nmov.b64 b, {%4, %5};\nmov.b64 c, {%0, %1};\n"
+      "fma.rn.f32x2 c, a, b, c;\nmov.b64 {%0, %1}, c;\n}"
+      : "+f"(cx), "+f"(cy)
+      : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+}
+//   (cx, cy) = (ax, ay) * (bx, by)
+__device__ __forceinline__ void fmul2(float ax, float ay, float bx, float by, float& cx, float& cy) {
+  asm("{\n.reg .b64 a, b, c;\nmov.b64 a, {%2, %3};\nmov.b64 b, {%4, %5};\n"
+      "mul.rn.f32x2 c, a, b;\nmov.b64 {%0, %1}, c;\n}"
+      : "=f"(cx), "=f"(cy)
+      : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+}
 // ---- mbarrier helpers (producer/consumer rings of the tcgen05 GEMM, gemm_tc.cuh) ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -16,8 +16,6 @@
 
 namespace cl3d {
 
-typedef unsigned long long u64;
-
 struct GridParams {
   float ox, oy, oz, inv_h;
   int gx, gy, gz, ncells;
@@ -259,8 +257,13 @@ __device__ __forceinline__ void emit_sorted(const u64* L, int cnt, int* s_sorted
 // L[0..cnt) holds the reference's candidate list (any order; unique indices).  Emits the first K of the list
 // sorted by (d2, index) -- identical to the reference's stable sort of an index-ascending list
 // (masked_ordered_ball_query_gpu.cu:77) -- then the cyclic padding (:83-86) and masks (:79-93).
+// csr_cnt (may be null): per-support-point reference counters of this cloud.  Every counted slot (k < ncount, or all K
+// slots with csr_all) takes its rank inside the support point's transposed list right here (one int atomic per
+// slot, K of them in flight per warp), so the list build that follows is a scan and an atomic-free scatter.
 __device__ __forceinline__ void emit_query(const u64* L, int cnt, int* s_sorted, int K, int qm, int* __restrict__ idx_out,
-                                           int* __restrict__ mask_out, int* __restrict__ ncount_out) {
+                                           int* __restrict__ mask_out, int* __restrict__ ncount_out,
+                                           int* __restrict__ csr_cnt = nullptr, int* __restrict__ rank_out = nullptr,
+                                           int csr_all = 0) {
   const int lane = lane_id();
   if (cnt <= 32) {
     emit_sorted<1>(L, cnt, s_sorted, K);
@@ -277,13 +280,15 @@ __device__ __forceinline__ void emit_query(const u64* L, int cnt, int* s_sorted,
     }
   }
   __syncwarp();
+  const int ncnt = qm != 0 ? (cnt < K ? cnt : K) : K;
   for (int k = lane; k < K; k += 32) {
     int v = 0;
     if (cnt > 0) v = s_sorted[k < cnt ? k : (k % cnt)];
     idx_out[k] = v;
     if (mask_out) mask_out[k] = (k < cnt && qm != 0) ? 1 : 0;
+    if (csr_cnt && (csr_all || k < ncnt)) rank_out[k] = atomicAdd(&csr_cnt[v], 1);
   }
-  if (ncount_out && lane == 0) *ncount_out = qm != 0 ? (cnt < K ? cnt : K) : K;
+  if (ncount_out && lane == 0) *ncount_out = ncnt;
   __syncwarp();
 }
 
@@ -336,7 +341,8 @@ __device__ __forceinline__ int brute_force_collect(LoadXYZ load, int n_valid, fl
 __global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
     const float* __restrict__ query_xyz, const float* __restrict__ support_xyz, const int* __restrict__ query_mask,
     const int* __restrict__ support_mask, int N, int M, float radius, int K, int queries_per_cta,
-    int* __restrict__ idx, int* __restrict__ idx_mask, int* __restrict__ ncount) {
+    int* __restrict__ idx, int* __restrict__ idx_mask, int* __restrict__ ncount, int* __restrict__ csr_cnt,
+    int* __restrict__ csr_rank, int csr_all) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.y;
   const int cap3k = 3 * K;
@@ -404,7 +410,8 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_brute_kernel(
     }
     const size_t o = ((size_t)b * M + q);
     emit_query(L, cnt, srt, K, query_mask[o], idx + o * K, idx_mask ? idx_mask + o * K : nullptr,
-               ncount ? ncount + o : nullptr);
+               ncount ? ncount + o : nullptr, csr_cnt ? csr_cnt + (size_t)b * N : nullptr,
+               csr_rank ? csr_rank + o * K : nullptr, csr_all);
   }
 }
 
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_grid_kernel(
     const float* __restrict__ query_xyz, const float* __restrict__ support_xyz, const int* __restrict__ query_mask,
     const GridParams* __restrict__ params, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
     int B, int N, int M, float radius, int K, int cell_cap, int* __restrict__ idx, int* __restrict__ idx_mask,
-    int* __restrict__ ncount) {
+    int* __restrict__ ncount, int* __restrict__ csr_cnt, int* __restrict__ csr_rank, int csr_all) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap3k = 3 * K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -479,6 +486,8 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_grid_kernel(
   int* io = idx + (size_t)gq * K;
   int* mo = idx_mask ? idx_mask + (size_t)gq * K : nullptr;
   int* no = ncount ? ncount + gq : nullptr;
+  int* cc = csr_cnt ? csr_cnt + (size_t)b * N : nullptr;
+  int* cr = csr_rank ? csr_rank + (size_t)gq * K : nullptr;
   if (T > kCandCap) {
     // neighbourhood does not fit on chip: exact index-order scan straight from global memory (rare)
     const float* sx = support_xyz + (size_t)b * N * 3;
@@ -489,11 +498,11 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_grid_kernel(
           z = sx[i * 3 + 2];
         },
         p.n_valid, qx, qy, qz, r2, cap3k, s_keep);
-    emit_query(s_keep, cnt, s_sorted, K, qm, io, mo, no);
+    emit_query(s_keep, cnt, s_sorted, K, qm, io, mo, no, cc, cr, csr_all);
     return;
   }
   if (T <= cap3k) {
-    emit_query(s_cand, T, s_sorted, K, qm, io, mo, no);
+    emit_query(s_cand, T, s_sorted, K, qm, io, mo, no, cc, cr, csr_all);
     return;
   }
   // more than 3K candidates: the reference keeps the 3K SMALLEST INDICES (it scans in index order, :64-68),
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(kBQWarps * 32) ball_query_grid_kernel(
     kept += __popc(m);
   }
   __syncwarp();
-  emit_query(s_keep, cap3k, s_sorted, K, qm, io, mo, no);
+  emit_query(s_keep, cap3k, s_sorted, K, qm, io, mo, no, cc, cr, csr_all);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -592,7 +601,7 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int N, const int* __rest
                                                         int* __restrict__ cursor) {
   const int b = blockIdx.x;
   cnt += (size_t)b * N;
-  cursor += (size_t)b * N;
+  if (cursor) cursor += (size_t)b * N;
   off += (size_t)b * (N + 1);
   __shared__ int s_warp[32];
   const int per = (N + blockDim.x - 1) / blockDim.x;
@@ -620,7 +629,7 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int N, const int* __rest
   int base = v - sum + ((threadIdx.x >> 5) > 0 ? s_warp[(threadIdx.x >> 5) - 1] : 0);
   for (int i = lo; i < hi; ++i) {
     off[i] = base;
-    cursor[i] = base;
+    if (cursor) cursor[i] = base;
     base += cnt[i];
   }
   if (threadIdx.x == blockDim.x - 1) off[N] = base;
@@ -636,6 +645,19 @@ __global__ void csr_fill_kernel(const int* __restrict__ idx, const int* __restri
   const int j = idx[((size_t)b * M + q) * K + k];
   const int pos = atomicAdd(&cursor[(size_t)b * N + j], 1);
   ent[(size_t)b * M * K + pos] = (int)e;
+}
+
+// lists from ranks taken during the search: ent[off[j] + rank] = entry id  (no atomics)
+__global__ void csr_place_kernel(const int* __restrict__ idx, const int* __restrict__ ncount,
+                                 const int* __restrict__ rank, const int* __restrict__ off, int N, int M, int K,
+                                 int csr_all, int* __restrict__ ent) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)M * K) return;
+  const int q = (int)(e / K), k = (int)(e % K);
+  if (!csr_all && k >= ncount[(size_t)b * M + q]) return;
+  const size_t g = (size_t)b * M * K + e;
+  ent[(size_t)b * M * K + off[(size_t)b * (N + 1) + idx[g]] + rank[g]] = (int)e;
 }
 
 }  // namespace cl3d
@@ -667,11 +689,58 @@ extern "C" int cl3d_ball_query(const float* query_xyz, const float* support_xyz,
                               ncount, workspace, workspace_bytes, CL3D_BQ_AUTO, stream_);
 }
 
+static int ball_query_impl(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                           const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
+                           int* idx_mask, int* ncount, void* workspace, size_t workspace_bytes, int algo,
+                           int* csr_cnt, int* csr_rank, int csr_all, cudaStream_t stream);
+
 extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support_xyz, const int* query_mask,
                                     const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
                                     int* idx_mask, int* ncount, void* workspace, size_t workspace_bytes, int algo,
                                     cl3d_stream_t stream_) {
+  return ball_query_impl(query_xyz, support_xyz, query_mask, support_mask, B, N, M, radius, K, idx, idx_mask, ncount,
+                         workspace, workspace_bytes, algo, nullptr, nullptr, 0, (cudaStream_t)stream_);
+}
+
+extern "C" size_t cl3d_ball_query_csr_workspace_bytes(int B, int N, int M, int K) {
+  return cl3d_ball_query_workspace_bytes(B, N, M, K) + align_up(sizeof(int) * (size_t)(B > 0 ? B : 1) * (size_t)N, 256) +
+         align_up(sizeof(int) * (size_t)(B > 0 ? B : 1) * (size_t)(M > 0 ? M : 1) * (size_t)K, 256);
+}
+
+extern "C" int cl3d_ball_query_csr(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                                   const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
+                                   int* idx_mask, int* ncount, int all_slots, int* csr_off, int* csr_ent,
+                                   void* workspace, size_t workspace_bytes, int algo, cl3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  CL3D_REQUIRE(csr_off && csr_ent && ncount, "cl3d_ball_query_csr: null pointer");
+  CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0 && K >= 1, "cl3d_ball_query_csr: bad sizes");
+  if (workspace_bytes < cl3d_ball_query_csr_workspace_bytes(B, N, M, K) || !workspace) {
+    set_error("cl3d_ball_query_csr: workspace too small");
+    return CL3D_ERR_WORKSPACE;
+  }
+  if (B == 0) return CL3D_OK;
+  const size_t bq = cl3d_ball_query_workspace_bytes(B, N, M, K);
+  int* cnt = (int*)((unsigned char*)workspace + bq);
+  int* rank = (int*)((unsigned char*)cnt + align_up(sizeof(int) * (size_t)B * N, 256));
+  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)B * N, stream);
+  if (M > 0) {
+    int rc = ball_query_impl(query_xyz, support_xyz, query_mask, support_mask, B, N, M, radius, K, idx, idx_mask, ncount,
+                             workspace, bq, algo, cnt, rank, all_slots ? 1 : 0, stream);
+    if (rc) return rc;
+  }
+  csr_scan_kernel<<<B, 1024, 0, stream>>>(N, cnt, csr_off, nullptr); CL3D_LAUNCHED(1);
+  const long long ents = (long long)M * K;
+  if (ents > 0) {
+    csr_place_kernel<<<dim3((unsigned)((ents + 255) / 256), B), 256, 0, stream>>>(idx, ncount, rank, csr_off, N, M, K,
+                                                                                  all_slots ? 1 : 0, csr_ent); CL3D_LAUNCHED(1);
+  }
+  return check_launch("ball query + transposed lists");
+}
+
+static int ball_query_impl(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                           const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
+                           int* idx_mask, int* ncount, void* workspace, size_t workspace_bytes, int algo,
+                           int* csr_cnt, int* csr_rank, int csr_all, cudaStream_t stream) {
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0 && K >= 1, "cl3d_ball_query: bad sizes B=%d N=%d M=%d K=%d", B, N, M, K);
   CL3D_REQUIRE(K <= 256, "cl3d_ball_query: nsample %d > 256 unsupported", K);
   CL3D_REQUIRE(query_xyz && support_xyz && query_mask && support_mask && idx, "cl3d_ball_query: null pointer");
@@ -689,7 +758,8 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
       cudaFuncSetAttribute(ball_query_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(ceil_div(M, qpc), B);
     ball_query_brute_kernel<<<grid, kBQWarps * 32, smem, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
-                                                                   N, M, radius, K, qpc, idx, idx_mask, ncount); CL3D_LAUNCHED(1);
+                                                                   N, M, radius, K, qpc, idx, idx_mask, ncount, csr_cnt,
+                                                                   csr_rank, csr_all); CL3D_LAUNCHED(1);
     return check_launch("ball_query_brute_kernel");
   }
   if (workspace_bytes < cl3d_ball_query_workspace_bytes(B, N, M, K) || !workspace) {
@@ -721,7 +791,8 @@ extern "C" int cl3d_ball_query_algo(const float* query_xyz, const float* support
     cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const long long total = (long long)B * M;
   ball_query_grid_kernel<<<(unsigned)((total + kBQWarps - 1) / kBQWarps), kBQWarps * 32, smem, stream>>>(
-      query_xyz, support_xyz, query_mask, params, cell_start, sorted, B, N, M, radius, K, cap, idx, idx_mask, ncount); CL3D_LAUNCHED(1);
+      query_xyz, support_xyz, query_mask, params, cell_start, sorted, B, N, M, radius, K, cap, idx, idx_mask, ncount,
+      csr_cnt, csr_rank, csr_all); CL3D_LAUNCHED(1);
   return check_launch("ball_query_grid_kernel");
 }
 

@@ -145,7 +145,8 @@ class PosPool(nn.Module):
                 rng = torch.arange(fd, dtype=torch.float32).to(support_features.device)
                 self._dim_mat = torch.pow(1.0 * 1000, (1.0 / fd) * rng).contiguous()
             p0 = self._dim_mat
-        nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, self.radius, self.nsample)
+        nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, self.radius, self.nsample,
+                                 csr="counted" if torch.is_grad_enabled() else None)
         spec = _AggSpec(fam, ops.REDUCE[self.reduction], self.radius, self.nsample, normalize=1)
         bn = self.out_transform[0]
         return _FusedAggBNReLU.apply(support_features.contiguous(), p0, None, bn.weight, bn.bias, spec, nl,
@@ -192,7 +193,8 @@ class AdaptiveWeight(nn.Module):
         C = support_features.shape[1]
         S = self.shared_channels
         conv = self.mlps.conv0
-        nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, self.radius, self.nsample)
+        nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, self.radius, self.nsample,
+                                 csr="counted" if torch.is_grad_enabled() else None)
         spec = _AggSpec(ops.FAM_ADAPTIVE_DP, ops.REDUCE[self.reduction], self.radius, self.nsample, normalize=1,
                         shared=S)
         bn = self.out_transform[0]
@@ -234,7 +236,8 @@ class PseudoGrid(nn.Module):
         if not self._fusable():
             return _composed.pseudo_grid(self, query_xyz, support_xyz, query_mask, support_mask, support_features)
         _check_inputs(query_xyz, support_xyz, query_mask, support_mask, support_features)
-        nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, self.radius, self.nsample)
+        nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, self.radius, self.nsample,
+                                 csr="counted" if torch.is_grad_enabled() else None)
         spec = _AggSpec(ops.FAM_PSEUDOGRID, ops.REDUCE["sum"], self.radius, self.nsample, normalize=0,
                         nkp=self.num_kernel_points, extent=self.extent,
                         influence=1 if self.KP_influence == "constant" else 0)

@@ -47,9 +47,11 @@ def _empty_pm(B, N, W, device):
 
 @_on_device
 def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_mask=True, want_ncount=True,
-               algo=0):
+               algo=0, csr=None):
     """-> (idx (B,M,K) i32, idx_mask (B,M,K) i32 | None, ncount (B,M) i32 | None); bit-exact with the
-    reference's masked_ordered_ball_query (masked_ordered_ball_query_gpu.cu:11-96)."""
+    reference's masked_ordered_ball_query (masked_ordered_ball_query_gpu.cu:11-96).
+    csr = "counted" | "all": also build the transposed lists in the same call (cl3d_ball_query_csr) and return
+    (idx, idx_mask, ncount, (csr_off, csr_ent))."""
     require_cuda(query_xyz, "query_xyz", F32)
     require_cuda(support_xyz, "support_xyz", F32)
     require_cuda(query_mask, "query_mask", I32)
@@ -61,7 +63,17 @@ def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample
     L = _lib.lib()
     idx = torch.empty(B, M, K, dtype=I32, device=dev)
     idx_mask = torch.empty(B, M, K, dtype=I32, device=dev) if want_mask else None
-    ncount = torch.empty(B, M, dtype=I32, device=dev) if want_ncount else None
+    ncount = torch.empty(B, M, dtype=I32, device=dev) if (want_ncount or csr) else None
+    if csr:
+        assert csr in ("counted", "all")
+        off = torch.empty(B, N + 1, dtype=I32, device=dev)
+        ent = torch.empty(B, M * K, dtype=I32, device=dev)
+        wsb = L.cl3d_ball_query_csr_workspace_bytes(B, N, M, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(L.cl3d_ball_query_csr(ptr(query_xyz), ptr(support_xyz), ptr(query_mask), ptr(support_mask), B, N, M,
+                                    float(radius), K, ptr(idx), ptr(idx_mask), ptr(ncount), 1 if csr == "all" else 0,
+                                    ptr(off), ptr(ent), ptr(ws), wsb, int(algo), stream_ptr()), "cl3d_ball_query_csr")
+        return idx, idx_mask, ncount, (off, ent)
     wsb = L.cl3d_ball_query_workspace_bytes(B, N, M, K)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     check(L.cl3d_ball_query_algo(ptr(query_xyz), ptr(support_xyz), ptr(query_mask), ptr(support_mask), B, N, M,

@@ -128,11 +128,14 @@ def clear_neighbor_cache():
     _CACHE.clear()
 
 
-def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, need_mask=False, overlap=None):
+def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, need_mask=False, overlap=None,
+              csr=None):
     """Ball-query neighbour list for (query, support, radius, nsample), cached on tensor identity
     (data pointer + version; the cache keeps the key tensors alive so pointers cannot be recycled).
     With overlap (default: pt_utils.overlap_enabled) the search runs on a side stream; consumers call
-    nl.wait() (the fused operators do) before touching nl.idx / nl.ncount."""
+    nl.wait() (the fused operators do) before touching nl.idx / nl.ncount.
+    csr = "counted" | "all": a backward will follow -- the transposed lists are built in the same call as the
+    search (ranks taken in its emit phase), not by a separate count / scan / fill afterwards."""
     key = (_key(query_xyz), _key(support_xyz), _key(query_mask), _key(support_mask), float(radius), int(nsample))
     if cache_enabled:
         hit = _CACHE.get(key)
@@ -142,21 +145,31 @@ def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
             return hit[0]
     cache_stats["miss"] += 1
     overlap = overlap_enabled if overlap is None else overlap
+    lists = None
     if overlap:
         cur = torch.cuda.current_stream()
         side = _side_stream(query_xyz.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            idx, idx_mask, ncount = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
-                                                   want_mask=need_mask, want_ncount=True)
+            res = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
+                                 want_mask=need_mask, want_ncount=True, csr=csr)
             ev = torch.cuda.Event()
             ev.record(side)
+        idx, idx_mask, ncount = res[:3]
+        lists = res[3] if csr else None
         nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
         nl.event = ev
     else:
-        idx, idx_mask, ncount = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
-                                               want_mask=need_mask, want_ncount=True)
+        res = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
+                             want_mask=need_mask, want_ncount=True, csr=csr)
+        idx, idx_mask, ncount = res[:3]
+        lists = res[3] if csr else None
         nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
+    if lists is not None:   # ready when the search event fires (csr() / csr_all_slots() wait for it)
+        if csr == "all":
+            nl._csr_all, nl._csr_all_event = lists, nl.event
+        else:
+            nl._csr, nl._csr_event = lists, nl.event
     if cache_enabled:
         _CACHE[key] = (nl, (query_xyz, support_xyz, query_mask, support_mask))
         while len(_CACHE) > _CACHE_SIZE:

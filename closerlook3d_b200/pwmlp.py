@@ -75,7 +75,10 @@ class _FusedPointWiseMLP(Function):
 
 
 def forward(module, query_xyz, support_xyz, query_mask, support_mask, support_features):
-    nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, module.radius, module.nsample)
     conv, bn = module.mlps.conv0[0], module.mlps.conv0[1]
+    # a differentiated forward in training mode needs the all-slots transposed lists (BatchNorm2d backward is dense)
+    need_lists = torch.is_grad_enabled() and (bn.training or bn.running_mean is None)
+    nl = pt_utils.neighbors(query_xyz, support_xyz, query_mask, support_mask, module.radius, module.nsample,
+                            csr="all" if need_lists else None)
     return _FusedPointWiseMLP.apply(support_features.contiguous(), conv.weight, bn.weight, bn.bias, nl, query_xyz,
                                     support_xyz, module.radius, bn)

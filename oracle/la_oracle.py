@@ -56,6 +56,25 @@ GPU_SCALAR_DIVISION = False
 # evaluates the reference's expression on the GPU (fd -> (fd,) float32 CPU tensor); None = evaluate on the CPU.
 DIM_MAT_FN = None
 
+# Checker-side diagnostics: when this is a dict, pointwise_mlp() leaves its pre-max activations (B,C,M,K) and the
+# neighbour indices (B,M,K) in it, so that a parity test can find the (query, channel) positions whose two best
+# DISTINCT neighbours are closer than the comparison tolerance -- there the arg-max, and with it the gradient
+# routing, is decided by rounding (see argmax_is_decided()).
+KEEP = None
+
+
+def argmax_is_decided(premax, idx, rel=2e-5):
+    """(B,C,M) bool: the largest activation over K beats the best activation of any OTHER neighbour by more than
+    rel * max(1, |value|).  Duplicated slots of the same neighbour (cyclic padding) do not count as competitors:
+    routing the gradient to either copy is the same gradient; neither does a maximum of 0 (ReLU output)."""
+    xs, order = premax.sort(dim=-1, descending=True)
+    ig = idx[:, None, :, :].expand(-1, premax.shape[1], -1, -1).gather(-1, order)
+    other = ig != ig[..., :1]
+    second = torch.where(other, xs, torch.full_like(xs, float("-inf"))).max(-1)[0]
+    v1 = xs[..., 0]
+    # the activations are post-ReLU: a maximum of exactly 0 passes no gradient whichever slot holds it
+    return ((v1 - second) > rel * v1.abs().clamp(min=1.0)) | (v1 <= 0)
+
 
 def query_and_group(ext, query_xyz, support_xyz, query_mask, support_mask, features, radius, nsample,
                     normalize_xyz):
@@ -187,12 +206,14 @@ def pointwise_mlp(ext, st, cfg, cin, cout, radius, nsample, q_xyz, s_xyz, q_mask
     pw = cfg.pointwisemlp
     if pw.feature_type != "dp_fi_df":                                         # :288-295
         raise NotImplementedError(pw.feature_type)
-    gf, dp, idx_mask, _ = query_and_group(ext, q_xyz, s_xyz, q_mask, s_mask, feats, radius, nsample, True)
+    gf, dp, idx_mask, idx = query_and_group(ext, q_xyz, s_xyz, q_mask, s_mask, feats, radius, nsample, True)
     center = gf[..., 0:1].expand(-1, -1, -1, nsample)                         # slot 0 = nearest neighbour
     x = torch.cat([dp, center, gf - center], 1)
     for i in range(pw.num_mlps):                                              # :252-272 conv + BN2d + ReLU
         x = F.conv2d(x, st[f"mlps.conv{i}.0.weight"])
         x = F.relu(_bn(x, st, f"mlps.conv{i}.1", cfg.bn_momentum, training))
+    if KEEP is not None:
+        KEEP["pwmlp_premax"], KEEP["idx"] = x.detach(), idx.long()
     return _reduce(x, idx_mask, q_mask, pw.reduction)                         # no out_transform (:297-316)
 
 

@@ -77,7 +77,16 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     orc.training = train
     od = oracle_device
     f_ref = feats.clone().to(od).requires_grad_(True)
+    la_oracle.KEEP = {} if (la_type == "pointwisemlp" and over["pointwisemlp"].get("reduction") == "max") else None
     o_ref = orc(q.to(od), xyz.to(od), qm.to(od), mask.to(od), f_ref)
+    decided = None
+    if la_oracle.KEEP:
+        # max over K: where the two best DISTINCT neighbours tie within the tolerance, rounding decides which one
+        # receives the gradient (a discontinuity like the ReLU's); those (query, channel) positions get no
+        # upstream gradient on either side
+        decided = la_oracle.argmax_is_decided(la_oracle.KEEP["pwmlp_premax"], la_oracle.KEEP["idx"]).cpu()
+        assert int((~decided).sum()) <= max(4, decided.numel() // 20000), f"{int((~decided).sum())} undecided maxima"
+    la_oracle.KEEP = None
     mod = mod.to(cuda)
     mod.train(train)
     f = feats.to(cuda).requires_grad_(True)
@@ -90,6 +99,8 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     flips = (out.detach().cpu() > 0) != (o_ref.detach().cpu() > 0)
     assert int(flips.sum()) <= max(2, out.numel() // 100000), f"{int(flips.sum())} ReLU sign flips"
     gout = gout * (~flips)
+    if decided is not None:
+        gout = gout * decided
     (o_ref * gout.to(od)).sum().backward()
     (out * gout.to(cuda)).sum().backward()
     torch.cuda.synchronize()
