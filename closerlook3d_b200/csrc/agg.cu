@@ -398,7 +398,7 @@ __host__ __device__ inline size_t pg_bwd_extra_floats(int CI) {
 }
 
 template <int FAM, int CI>
-__global__ void __launch_bounds__(kAggWarps * 32, FAM == CL3D_FAM_PSEUDOGRID ? 2 : 1) agg_bwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, (FAM == CL3D_FAM_PSEUDOGRID || CI > 3) ? 2 : 3) agg_bwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * 32 * CI;
@@ -628,36 +628,24 @@ __device__ __forceinline__ float div_by(float n, float d, float rcp_d) {
   return q;
 }
 
-// Two arguments at once (the same wave length for two neighbour slots), all arithmetic packed fp32x2: the same
-// Cody-Waite reduction and polynomials as sincos_small, with the nearest integer taken by the magic-number add
-// (t = x * 2/pi + 1.5 * 2^23: the integer sits in the low mantissa bits, so no F2I / FRND on the slow pipe) and the
-// sin and cos polynomials evaluated side by side.  7 FMA-pipe instructions per (neighbour, wave length) instead of 25.
+// sin and cos of two arguments at once (the same wave length for two neighbour slots).  ncu on the polynomial version
+// (profiles/r2h_sincos_summary.md): 34 instructions per (neighbour, wave length) evaluation, issue-bound, 10 of them
+// packed polynomial steps and 8 the quadrant swap / sign logic.  Here the argument is reduced EXACTLY (Cody-Waite with
+// a three-term 2*pi, packed; the nearest integer by the magic-number add, no F2I / FRND) to r in [-pi, pi], where the
+// hardware approximations are specified to 2^-21.4 (sin) / 2^-21.2 (cos) absolute error -- 4e-7, with the averaging over
+// the K neighbours well inside the 1e-5 parity bar (measured in tests/test_local_aggregation_gpu.py) -- and cost one
+// MUFU each: no polynomials, no quadrant logic.
 __device__ __forceinline__ void sincos_small2(u64 x2, u64& sn2, u64& cs2) {
   const float kMagic = 12582912.f;  // 1.5 * 2^23
-  const u64 t2 = fma2(x2, pack2(0.636619747f, 0.636619747f), pack2(kMagic, kMagic));
-  const u64 j2 = sub2(t2, pack2(kMagic, kMagic));
-  u64 r2v = fma2(j2, pack2(-1.57079601e+00f, -1.57079601e+00f), x2);
-  r2v = fma2(j2, pack2(-3.13916473e-07f, -3.13916473e-07f), r2v);
-  r2v = fma2(j2, pack2(-5.39030253e-15f, -5.39030253e-15f), r2v);
-  const u64 rr = mul2(r2v, r2v);
-  u64 ps = fma2(rr, pack2(-1.95152959e-4f, -1.95152959e-4f), pack2(8.33216087e-3f, 8.33216087e-3f));
-  ps = fma2(ps, rr, pack2(-1.66666546e-1f, -1.66666546e-1f));
-  ps = fma2(mul2(ps, rr), r2v, r2v);                                           // sin(r)
-  u64 pc = fma2(rr, pack2(2.44331571e-5f, 2.44331571e-5f), pack2(-1.38873163e-3f, -1.38873163e-3f));
-  pc = fma2(pc, rr, pack2(4.16666457e-2f, 4.16666457e-2f));
-  pc = fma2(pc, rr, pack2(-0.5f, -0.5f));
-  pc = fma2(pc, rr, pack2(1.0f, 1.0f));                                        // cos(r)
-  float ta, tb, sa, sb, ca, cb;
-  unpack2(t2, ta, tb);
-  unpack2(ps, sa, sb);
-  unpack2(pc, ca, cb);
-  const unsigned qa = __float_as_uint(ta), qb = __float_as_uint(tb);            // quadrant = low two bits
-  const float s0a = (qa & 1u) ? ca : sa, c0a = (qa & 1u) ? sa : ca;
-  const float s0b = (qb & 1u) ? cb : sb, c0b = (qb & 1u) ? sb : cb;
-  sn2 = pack2(__uint_as_float(__float_as_uint(s0a) ^ ((qa << 30) & 0x80000000u)),
-              __uint_as_float(__float_as_uint(s0b) ^ ((qb << 30) & 0x80000000u)));
-  cs2 = pack2(__uint_as_float(__float_as_uint(c0a) ^ (((qa + 1u) << 30) & 0x80000000u)),
-              __uint_as_float(__float_as_uint(c0b) ^ (((qb + 1u) << 30) & 0x80000000u)));
+  const u64 t2 = fma2(x2, pack2(0.15915494309f, 0.15915494309f), pack2(kMagic, kMagic));   // x / (2 pi) + magic
+  const u64 j2 = sub2(t2, pack2(kMagic, kMagic));                                         // nearest integer
+  u64 r2v = fma2(j2, pack2(-6.28318548202514648e+00f, -6.28318548202514648e+00f), x2);    // 2 pi = hi + mid + lo
+  r2v = fma2(j2, pack2(1.74845553146951715e-07f, 1.74845553146951715e-07f), r2v);
+  r2v = fma2(j2, pack2(7.1054273576010019e-15f, 7.1054273576010019e-15f), r2v);
+  float ra, rb;
+  unpack2(r2v, ra, rb);
+  sn2 = pack2(__sinf(ra), __sinf(rb));
+  cs2 = pack2(__cosf(ra), __cosf(rb));
 }
 
 template <int PI, bool BWD>
@@ -674,31 +662,44 @@ __device__ __forceinline__ void consume_pairs(const float* __restrict__ base, co
     rd2[i] = pack2(pl.rdim[i], pl.rdim[i]);
   }
   const u64 hundred = pack2(100.f, 100.f);
-  int s = 0;
-  for (; s + 2 <= n; s += 2) {
-    const float4 dp0 = s_dp[s], dp1 = s_dp[s + 1];
-    const unsigned o0 = __float_as_uint(dp0.w), o1 = __float_as_uint(dp1.w);   // row element offsets
-    u64 vs2[PI], vc2[PI];
+  // The gathered values of slot pair s+2 are requested BEFORE the arithmetic of slot pair s (software pipeline, one
+  // pair deep): in the r2h profile a third of the stall samples sat on the accumulate FFMA2s waiting for loads that
+  // had been issued ~45 instructions earlier -- an L2 hit takes several hundred cycles.
+  auto gather = [&](int s0, u64 (&vs2)[PI], u64 (&vc2)[PI]) {
+    const unsigned o0 = __float_as_uint(s_dp[s0].w), o1 = __float_as_uint(s_dp[s0 + 1].w);   // row element offsets
 #pragma unroll
     for (int i = 0; i < PI; ++i) {  // one 32-bit add + one IMAD.WIDE per address (row_at)
       vs2[i] = pack2(__ldg(row_at(base, o0 + pl.osin[i])), __ldg(row_at(base, o1 + pl.osin[i])));
       vc2[i] = pack2(__ldg(row_at(base, o0 + pl.ocos[i])), __ldg(row_at(base, o1 + pl.ocos[i])));
     }
+  };
+  const int n2 = n & ~1;
+  u64 vs2[PI], vc2[PI], nvs2[PI], nvc2[PI];
+  if (n2 > 0) gather(0, vs2, vc2);
+  int s = 0;
+  for (; s < n2; s += 2) {
+    if (s + 2 < n2) gather(s + 2, nvs2, nvc2);
+    const float4 dp0 = s_dp[s], dp1 = s_dp[s + 1];
     u64 sc2 = 0ull;
     if constexpr (BWD) sc2 = pack2(s_h[s], s_h[s + 1]);
     const u64 px = mul2(pack2(dp0.x, dp1.x), hundred), py = mul2(pack2(dp0.y, dp1.y), hundred),
               pz = mul2(pack2(dp0.z, dp1.z), hundred);   // alpha * dp  (:75)
 #pragma unroll
     for (int i = 0; i < PI; ++i) {
-      const u64 n2 = pl.axis[i] == 0 ? px : (pl.axis[i] == 1 ? py : pz);
+      const u64 n2v = pl.axis[i] == 0 ? px : (pl.axis[i] == 1 ? py : pz);
       // torch.div(alpha * dp, dim_mat): correctly rounded quotient, two Markstein corrections (see div_by)
-      u64 q2 = mul2(n2, rd2[i]);
-      q2 = fma2(fma2(nd2[i], q2, n2), rd2[i], q2);
-      q2 = fma2(fma2(nd2[i], q2, n2), rd2[i], q2);
+      u64 q2 = mul2(n2v, rd2[i]);
+      q2 = fma2(fma2(nd2[i], q2, n2v), rd2[i], q2);
+      q2 = fma2(fma2(nd2[i], q2, n2v), rd2[i], q2);
       u64 sn2, cs2;
       sincos_small2(q2, sn2, cs2);
       as2[i] = fma2(BWD ? mul2(vs2[i], sc2) : vs2[i], sn2, as2[i]);
       ac2[i] = fma2(BWD ? mul2(vc2[i], sc2) : vc2[i], cs2, ac2[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < PI; ++i) {
+      vs2[i] = nvs2[i];
+      vc2[i] = nvc2[i];
     }
   }
 #pragma unroll
@@ -734,7 +735,7 @@ __device__ __forceinline__ int pair_row_channel(int r, int p0, int pairs_per_cta
 }
 
 template <int PI>
-__global__ void __launch_bounds__(kAggWarps * 32) sincos_fwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, 2) sincos_fwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p0 = blockIdx.y * 32 * PI;
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) sincos_fwd_kernel(const AggArg
 }
 
 template <int PI>
-__global__ void __launch_bounds__(kAggWarps * 32) sincos_bwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, 2) sincos_bwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p0 = blockIdx.y * 32 * PI;

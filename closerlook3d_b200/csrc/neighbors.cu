@@ -12,6 +12,8 @@
 // (first 3K in-radius points by index, nearest-overwrite rule, stable sort by distance, cyclic padding);
 // that rule is reproduced on the candidate set with 64-bit keys (d2 bits << 32 | index), which order
 // exactly like the reference's stable sort because candidates are unique in index.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cl3d {
@@ -196,6 +198,164 @@ __global__ void cell_fill_kernel(const float* __restrict__ xyz, const GridParams
   int2 cr = cell_rank[(size_t)b * N + i];
   int pos = cell_start[(size_t)b * (cell_cap + 1) + cr.x] + cr.y;
   sorted[(size_t)b * N + pos] = make_float4(q[0], q[1], q[2], __int_as_float(i));
+}
+
+// Whole grid build of one cloud in ONE kernel (one CTA of 1024 threads per cloud) when the cell counters fit in
+// shared memory: valid prefix + bounding box + grid dimensions, cell counts with shared-memory atomics, exclusive scan,
+// scatter into cell order.  The BASELINE clouds have 10^3 .. 15^3 cells, so this replaces the five dependent launches
+// (params, zero, count, scan, fill: ~40 us of mostly launch latency at c3, r1n launch list) on the search's critical
+// path.  Larger grids use the same kernel with the counters in global memory.
+constexpr int kFusedGridCells = 12288;   // 48 KB of counters
+
+__device__ __forceinline__ GridParams make_grid_params(int nv, const float (&mn)[3], const float (&mx)[3], float radius,
+                                                       int cell_cap) {
+  GridParams p;
+  p.n_valid = nv;
+  p.pad0 = p.pad1 = p.pad2 = 0;
+  if (nv == 0) {
+    p.ox = p.oy = p.oz = 0.f;
+    p.inv_h = 1.f;
+    p.gx = p.gy = p.gz = 1;
+    p.ncells = 1;
+    return p;
+  }
+  const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+  // cell edge strictly larger than the radius: two points closer than `radius` along an axis then land
+  // in the same or adjacent cells even after fp32 rounding of the cell coordinate (< 512 per axis).
+  float h = radius * 1.001f;
+  if (!(h > 1e-20f)) h = 1e-20f;
+  int gx = 1, gy = 1, gz = 1;
+  for (int it = 0; it < 400; ++it) {  // bounded: non-finite coordinates fall back to a single cell
+    const float fx = fminf(ex / h, 510.f), fy = fminf(ey / h, 510.f), fz = fminf(ez / h, 510.f);
+    const int tx = (int)fx + 1, ty = (int)fy + 1, tz = (int)fz + 1;
+    if ((long long)tx * ty * tz <= (long long)cell_cap && ex / h < 511.f && ey / h < 511.f && ez / h < 511.f) {
+      gx = tx;
+      gy = ty;
+      gz = tz;
+      break;
+    }
+    h *= 1.25f;
+  }
+  p.ox = mn[0];
+  p.oy = mn[1];
+  p.oz = mn[2];
+  p.inv_h = 1.0f / h;
+  p.gx = gx;
+  p.gy = gy;
+  p.gz = gz;
+  p.ncells = gx * gy * gz;
+  return p;
+}
+
+__global__ void __launch_bounds__(1024) grid_build_fused_kernel(const float* __restrict__ xyz, const int* __restrict__ mask,
+                                                                int N, float radius, int cell_cap,
+                                                                GridParams* __restrict__ params,
+                                                                int* __restrict__ cell_cnt, int* __restrict__ cell_start,
+                                                                int2* __restrict__ cell_rank, float4* __restrict__ sorted) {
+  extern __shared__ int s_cnt_smem[];  // kFusedGridCells counters, then reused as the cell starts
+  const int b = blockIdx.x;
+  xyz += (size_t)b * N * 3;
+  mask += (size_t)b * N;
+  cell_start += (size_t)b * (cell_cap + 1);
+  cell_rank += (size_t)b * N;
+  sorted += (size_t)b * N;
+  __shared__ int s_first;
+  __shared__ float s_red[6][32];
+  __shared__ GridParams s_p;
+  __shared__ int s_warp[32];
+  if (threadIdx.x == 0) s_first = N;
+  __syncthreads();
+  int first = N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (mask[i] == 0) { first = i; break; }
+  if (first < N) atomicMin(&s_first, first);
+  __syncthreads();
+  const int nv = s_first;
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = xyz[i * 3 + a];
+      mn[a] = fminf(mn[a], v);
+      mx[a] = fmaxf(mx[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_red[a][threadIdx.x >> 5] = mn[a];
+      s_red[3 + a][threadIdx.x >> 5] = mx[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float gmn[3], gmx[3];
+    for (int a = 0; a < 3; ++a) {
+      gmn[a] = s_red[a][0];
+      gmx[a] = s_red[3 + a][0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        gmn[a] = fminf(gmn[a], s_red[a][w]);
+        gmx[a] = fmaxf(gmx[a], s_red[3 + a][w]);
+      }
+    }
+    s_p = make_grid_params(nv, gmn, gmx, radius, cell_cap);
+    params[b] = s_p;
+  }
+  __syncthreads();
+  const GridParams p = s_p;
+  // counters in shared memory when they fit (every BASELINE cloud), else in this cloud's slice of the global buffer
+  int* s_cnt = p.ncells <= kFusedGridCells ? s_cnt_smem : cell_cnt + (size_t)b * cell_cap;
+  for (int c = threadIdx.x; c < p.ncells; c += blockDim.x) s_cnt[c] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const int cx = cell_coord(xyz[i * 3 + 0], p.ox, p.inv_h, p.gx);
+    const int cy = cell_coord(xyz[i * 3 + 1], p.oy, p.inv_h, p.gy);
+    const int cz = cell_coord(xyz[i * 3 + 2], p.oz, p.inv_h, p.gz);
+    const int cell = cx + p.gx * (cy + p.gy * cz);
+    cell_rank[i] = make_int2(cell, atomicAdd(&s_cnt[cell], 1));
+  }
+  __syncthreads();
+  // exclusive scan of the counters, in place
+  const int per = (p.ncells + blockDim.x - 1) / blockDim.x;
+  const int lo = min((int)threadIdx.x * per, p.ncells), hi = min(lo + per, p.ncells);
+  int sum = 0;
+  for (int c = lo; c < hi; ++c) sum += s_cnt[c];
+  int v = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += t;
+    }
+    s_warp[threadIdx.x] = w;
+  }
+  __syncthreads();
+  int base = v - sum + ((threadIdx.x >> 5) > 0 ? s_warp[(threadIdx.x >> 5) - 1] : 0);
+  for (int c = lo; c < hi; ++c) {
+    const int n = s_cnt[c];
+    s_cnt[c] = base;
+    cell_start[c] = base;
+    base += n;
+  }
+  if (threadIdx.x == blockDim.x - 1) cell_start[p.ncells] = base;  // == n_valid
+  __syncthreads();
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const int2 cr = cell_rank[i];
+    sorted[s_cnt[cr.x] + cr.y] = make_float4(xyz[i * 3 + 0], xyz[i * 3 + 1], xyz[i * 3 + 2], __int_as_float(i));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -710,8 +870,10 @@ extern "C" size_t cl3d_ball_query_csr_workspace_bytes(int B, int N, int M, int K
 extern "C" int cl3d_ball_query_csr(const float* query_xyz, const float* support_xyz, const int* query_mask,
                                    const int* support_mask, int B, int N, int M, float radius, int K, int* idx,
                                    int* idx_mask, int* ncount, int all_slots, int* csr_off, int* csr_ent,
-                                   void* workspace, size_t workspace_bytes, int algo, cl3d_stream_t stream_) {
+                                   void* workspace, size_t workspace_bytes, int algo, int phases,
+                                   cl3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  CL3D_REQUIRE(phases >= 1 && phases <= 3, "cl3d_ball_query_csr: phases is a mask of 1 (search) | 2 (lists)");
   CL3D_REQUIRE(csr_off && csr_ent && ncount, "cl3d_ball_query_csr: null pointer");
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0 && K >= 1, "cl3d_ball_query_csr: bad sizes");
   if (workspace_bytes < cl3d_ball_query_csr_workspace_bytes(B, N, M, K) || !workspace) {
@@ -722,12 +884,15 @@ extern "C" int cl3d_ball_query_csr(const float* query_xyz, const float* support_
   const size_t bq = cl3d_ball_query_workspace_bytes(B, N, M, K);
   int* cnt = (int*)((unsigned char*)workspace + bq);
   int* rank = (int*)((unsigned char*)cnt + align_up(sizeof(int) * (size_t)B * N, 256));
-  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)B * N, stream);
-  if (M > 0) {
-    int rc = ball_query_impl(query_xyz, support_xyz, query_mask, support_mask, B, N, M, radius, K, idx, idx_mask, ncount,
-                             workspace, bq, algo, cnt, rank, all_slots ? 1 : 0, stream);
-    if (rc) return rc;
+  if (phases & 1) {
+    cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)B * N, stream);
+    if (M > 0) {
+      int rc = ball_query_impl(query_xyz, support_xyz, query_mask, support_mask, B, N, M, radius, K, idx, idx_mask,
+                               ncount, workspace, bq, algo, cnt, rank, all_slots ? 1 : 0, stream);
+      if (rc) return rc;
+    }
   }
+  if (!(phases & 2)) return check_launch("ball query (ranked)");
   csr_scan_kernel<<<B, 1024, 0, stream>>>(N, cnt, csr_off, nullptr); CL3D_LAUNCHED(1);
   const long long ents = (long long)M * K;
   if (ents > 0) {
@@ -779,12 +944,20 @@ static int ball_query_impl(const float* query_xyz, const float* support_xyz, con
   w += align_up(sizeof(int2) * (size_t)B * N, 256);
   float4* sorted = (float4*)w;
 
-  grid_params_kernel<<<B, 1024, 0, stream>>>(support_xyz, support_mask, N, radius, cap, params); CL3D_LAUNCHED(1);
-  zero_cells_kernel<<<dim3(64, B), 256, 0, stream>>>(params, cap, cell_cnt); CL3D_LAUNCHED(1);
-  cell_count_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_cnt, cell_rank); CL3D_LAUNCHED(1);
-  cell_scan_kernel<<<B, 1024, 0, stream>>>(params, cap, cell_cnt, cell_start); CL3D_LAUNCHED(1);
-  cell_fill_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_start, cell_rank,
-                                                                  sorted); CL3D_LAUNCHED(1);
+  if (getenv("CL3D_GRID_BUILD_V1")) {  // A/B switch: the five-kernel build
+    grid_params_kernel<<<B, 1024, 0, stream>>>(support_xyz, support_mask, N, radius, cap, params); CL3D_LAUNCHED(1);
+    zero_cells_kernel<<<dim3(64, B), 256, 0, stream>>>(params, cap, cell_cnt); CL3D_LAUNCHED(1);
+    cell_count_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_cnt, cell_rank); CL3D_LAUNCHED(1);
+    cell_scan_kernel<<<B, 1024, 0, stream>>>(params, cap, cell_cnt, cell_start); CL3D_LAUNCHED(1);
+    cell_fill_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(support_xyz, params, N, cap, cell_start, cell_rank,
+                                                                    sorted); CL3D_LAUNCHED(1);
+  } else {
+    static std::atomic<unsigned long long> attr_build{0};
+    allow_big_smem(grid_build_fused_kernel, attr_build);
+    grid_build_fused_kernel<<<B, 1024, kFusedGridCells * sizeof(int), stream>>>(support_xyz, support_mask, N, radius, cap,
+                                                                                params, cell_cnt, cell_start, cell_rank,
+                                                                                sorted); CL3D_LAUNCHED(1);
+  }
   size_t smem = (size_t)kBQWarps * (kCandCap + cap3k) * 8 + (size_t)kBQWarps * K * 4;
   static std::atomic<unsigned long long> attr_grid{0};
   if (first_call_on_device(attr_grid))

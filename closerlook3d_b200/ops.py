@@ -47,11 +47,12 @@ def _empty_pm(B, N, W, device):
 
 @_on_device
 def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_mask=True, want_ncount=True,
-               algo=0, csr=None):
+               algo=0, csr=None, after_search=None):
     """-> (idx (B,M,K) i32, idx_mask (B,M,K) i32 | None, ncount (B,M) i32 | None); bit-exact with the
     reference's masked_ordered_ball_query (masked_ordered_ball_query_gpu.cu:11-96).
     csr = "counted" | "all": also build the transposed lists in the same call (cl3d_ball_query_csr) and return
-    (idx, idx_mask, ncount, (csr_off, csr_ent))."""
+    (idx, idx_mask, ncount, (csr_off, csr_ent)).  after_search(): called between the search and the list build (the
+    caller records its "search done" event there, so consumers of idx do not wait for the lists)."""
     require_cuda(query_xyz, "query_xyz", F32)
     require_cuda(support_xyz, "support_xyz", F32)
     require_cuda(query_mask, "query_mask", I32)
@@ -70,9 +71,14 @@ def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample
         ent = torch.empty(B, M * K, dtype=I32, device=dev)
         wsb = L.cl3d_ball_query_csr_workspace_bytes(B, N, M, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        check(L.cl3d_ball_query_csr(ptr(query_xyz), ptr(support_xyz), ptr(query_mask), ptr(support_mask), B, N, M,
-                                    float(radius), K, ptr(idx), ptr(idx_mask), ptr(ncount), 1 if csr == "all" else 0,
-                                    ptr(off), ptr(ent), ptr(ws), wsb, int(algo), stream_ptr()), "cl3d_ball_query_csr")
+        args = (ptr(query_xyz), ptr(support_xyz), ptr(query_mask), ptr(support_mask), B, N, M, float(radius), K, ptr(idx),
+                ptr(idx_mask), ptr(ncount), 1 if csr == "all" else 0, ptr(off), ptr(ent), ptr(ws), wsb, int(algo))
+        if after_search is None:
+            check(L.cl3d_ball_query_csr(*args, 3, stream_ptr()), "cl3d_ball_query_csr")
+        else:
+            check(L.cl3d_ball_query_csr(*args, 1, stream_ptr()), "cl3d_ball_query_csr (search)")
+            after_search()
+            check(L.cl3d_ball_query_csr(*args, 2, stream_ptr()), "cl3d_ball_query_csr (lists)")
         return idx, idx_mask, ncount, (off, ent)
     wsb = L.cl3d_ball_query_workspace_bytes(B, N, M, K)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)

@@ -151,10 +151,16 @@ def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
         side = _side_stream(query_xyz.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
+            ev = torch.cuda.Event()          # search done: idx / ncount final (the forward kernels wait for this one)
             res = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
-                                 want_mask=need_mask, want_ncount=True, csr=csr)
-            ev = torch.cuda.Event()
-            ev.record(side)
+                                 want_mask=need_mask, want_ncount=True, csr=csr,
+                                 after_search=(lambda: ev.record(side)) if csr else None)
+            ev_lists = None
+            if csr:                          # lists done: only the backward waits for this one
+                ev_lists = torch.cuda.Event()
+                ev_lists.record(side)
+            else:
+                ev.record(side)
         idx, idx_mask, ncount = res[:3]
         lists = res[3] if csr else None
         nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
@@ -165,11 +171,12 @@ def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
         idx, idx_mask, ncount = res[:3]
         lists = res[3] if csr else None
         nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
-    if lists is not None:   # ready when the search event fires (csr() / csr_all_slots() wait for it)
+    if lists is not None:
+        lists_event = ev_lists if overlap else None    # in-order on the current stream without overlap
         if csr == "all":
-            nl._csr_all, nl._csr_all_event = lists, nl.event
+            nl._csr_all, nl._csr_all_event = lists, lists_event
         else:
-            nl._csr, nl._csr_event = lists, nl.event
+            nl._csr, nl._csr_event = lists, lists_event
     if cache_enabled:
         _CACHE[key] = (nl, (query_xyz, support_xyz, query_mask, support_mask))
         while len(_CACHE) > _CACHE_SIZE:

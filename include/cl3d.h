@@ -99,12 +99,15 @@ int cl3d_nearest_query(const float* query_xyz, const float* support_xyz, const i
  * takes its rank inside its support point's list during the search's emit phase (int atomics), so the list build is
  * a scan plus an atomic-free scatter instead of count + scan + atomic fill.  all_slots = 0: lists over the counted
  * slots k < ncount (avg / sum families); 1: over all K slots (PointWiseMLP: BatchNorm2d sees every slot).
- * csr_off (B,N+1), csr_ent (B,M*K) as cl3d_build_csr.  List order = atomic arrival order (not deterministic). */
+ * csr_off (B,N+1), csr_ent (B,M*K) as cl3d_build_csr.  List order = atomic arrival order (not deterministic).
+ * phases: 1 = the search (idx / idx_mask / ncount final, ranks left in the workspace), 2 = the lists from those ranks,
+ * 3 = both.  A caller that overlaps the list build with the forward kernels issues phase 1, records its "search done"
+ * event, then issues phase 2 with the same workspace. */
 size_t cl3d_ball_query_csr_workspace_bytes(int B, int N, int M, int K);
 int cl3d_ball_query_csr(const float* query_xyz, const float* support_xyz, const int* query_mask,
                         const int* support_mask, int B, int N, int M, float radius, int K, int* idx, int* idx_mask,
                         int* ncount, int all_slots, int* csr_off, int* csr_ent, void* workspace,
-                        size_t workspace_bytes, int algo, cl3d_stream_t stream);
+                        size_t workspace_bytes, int algo, int phases, cl3d_stream_t stream);
 
 /* Transposed neighbour lists ("who gathers me"), used by the gather-form backward kernels:
  *   csr_off (B,N+1) int32  out: entries of support point j of cloud b are csr_ent[b][off[j]..off[j+1])
