@@ -591,6 +591,31 @@ def config_dict(workload, spec, B_local, world):
                   "inputs in L2"}
 
 
+def shutdown_distributed(world, *graph_holders):
+    """Leave torch.distributed cleanly.  CUDA graphs that captured NCCL collectives hold references on the
+    communicator and ncclCommDestroy waits for them (measured: destroy_process_group() never returned while a
+    GraphedStep with an in-graph all-reduce was alive), so every graph is released first; a watchdog ends the
+    process if the teardown still stalls -- the JSON line has been printed by then."""
+    if world <= 1:
+        return
+    import gc
+    for h in graph_holders:
+        if isinstance(h, dict):
+            for k in ("gs", "mod", "ring", "gout"):
+                h.pop(k, None)
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    finally:
+        t.cancel()
+
+
 def step_algo_bytes_per_point(C, K):
     """compulsory HBM traffic of a fused fwd+bwd step, bytes per point"""
     return 16 * C + 8 * K + 32
@@ -660,9 +685,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 extra[f"c{ci}"] = {"workload": workload_of(sp, ci), "error": str(e)[:200]}
     if rank != 0:
-        if world > 1:
-            torch.distributed.barrier()
-            torch.distributed.destroy_process_group()
+        shutdown_distributed(world, res)
         return 0
 
     peak, peak_src = peaks()
@@ -722,9 +745,7 @@ def main():
             "clocks": clocks, "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches_per_step"],
             "e2e": e2e, "roofline": roof, "cpu_baseline": cb, "kernels": kern[:8], "configs": extra, "ref_gpu": rg}
     print(json.dumps(line))
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+    shutdown_distributed(world, res)
     return 0
 
 

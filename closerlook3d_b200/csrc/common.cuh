@@ -43,8 +43,14 @@ inline bool first_call_on_device(std::atomic<unsigned long long>& seen) {
 constexpr int kMaxDynSmem = 227 * 1024;
 template <typename K>
 inline void allow_big_smem(K kernel, std::atomic<unsigned long long>& seen) {
-  if (first_call_on_device(seen))
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (first_call_on_device(seen)) {
+    // the 227 KB limit covers static + dynamic shared memory of the block
+    cudaFuncAttributes fa;
+    int stat = 0;
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem - stat) != cudaSuccess)
+      cudaGetLastError();  // reported by the launch that follows if the kernel really needs it
+  }
 }
 __host__ __device__ inline int padded_channels(int C) { return (C + 7) & ~7; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

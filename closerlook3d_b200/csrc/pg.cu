@@ -25,6 +25,11 @@
 //   * the backward uses the same one-accumulator w-form for d/df and adds d/dWk into a per-warp shared-memory
 //     accumulator addressed by the entry's offset: ~64 registers instead of 127.
 // One warp per centre point, 32 centre points per CTA tile; the backward is a persistent tile loop.
+//
+// Tried and measured on the same inputs, not shipped (profiles/RESULTS_r2.md): kernel weights and d/dWk accumulators
+// resident in registers with dense kernel-point quads (3x fewer shared-memory wavefronts, but 128 / 168 registers: 16 / 10
+// warps per SM cannot hide the load latencies -- 0.31 / 0.66 ms forward / backward at c3 against 0.27 / 0.48 here, and
+// 0.33 / 0.84 with a cross-point software pipeline that spilled).
 #include <stdlib.h>
 
 #include "agg_common.cuh"
@@ -364,6 +369,7 @@ bool pg2_supported(const AggArgs& a) {
 
 int pg2_launch_fwd(const AggArgs& a, cudaStream_t stream) {
   if (!pg2_supported(a)) return CL3D_ERR_UNSUPPORTED;
+
   const PgSmem L = pg_smem(a.Cp, false);
   static std::atomic<unsigned long long> seen{0};
   allow_big_smem(pg2_kernel<false>, seen);
@@ -374,6 +380,7 @@ int pg2_launch_fwd(const AggArgs& a, cudaStream_t stream) {
 
 int pg2_launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   if (!pg2_supported(a)) return CL3D_ERR_UNSUPPORTED;
+
   const PgSmem L = pg_smem(a.Cp, true);
   static std::atomic<unsigned long long> seen{0};
   allow_big_smem(pg2_kernel<true>, seen);

@@ -99,10 +99,23 @@ def test_whole_model_matches_reference_gpu_path(cuda, ref_ext, task, la, over):
     (out * g).sum().backward()
     torch.cuda.synchronize()
     og = orc.grads()
+    # parameter gradients against ONE scale (the largest gradient norm of the network): several parameters have an
+    # analytically zero gradient (a bias in front of a BatchNorm) and hold pure rounding noise on both sides
+    gscale = max(float(v.norm()) for v in og.values())
     m = {"logits_l2": rel_l2(out, out_o), "logits_max": rel_max(out, out_o),
          "dfeat_l2": rel_l2(f.grad, f_o.grad), "dfeat_max": rel_max(f.grad, f_o.grad),
-         "dparam_l2": max(rel_l2(p.grad, og[n]) for n, p in model.named_parameters()),
-         "dparam_max": max(rel_max(p.grad, og[n]) for n, p in model.named_parameters())}
+         "dparam_l2": max(float((p.grad - og[n]).norm()) for n, p in model.named_parameters()) / gscale}
+    # How sensitive is the REFERENCE network's own gradient to rounding-level noise?  Perturb the input features by
+    # 1e-6 (relative) and differentiate the restated reference again: the gradient of a deep ReLU / max network with
+    # training-mode BatchNorms moves by far more than 1e-6.  That measured sensitivity is the yardstick for the
+    # gradient comparison (the forward values are compared at rounding level directly).
+    orc2 = model_oracle.OracleModel(ref_ext, cfg, sd, task, device=cuda)
+    gen = torch.Generator(device=cuda).manual_seed(9)
+    f_p = (feats * (1.0 + 1e-6 * torch.randn(feats.shape, device=cuda, generator=gen))).requires_grad_(True)
+    (orc2(xyz, mask, f_p) * g).sum().backward()
+    og2 = orc2.grads()
+    m["ref_sens_dfeat_l2"] = rel_l2(f_p.grad, f_o.grad)
+    m["ref_sens_dparam_l2"] = max(float((og2[n] - og[n]).norm()) for n in og) / gscale
     msd = model.state_dict()
     m["running_stats"] = max(rel_max(msd[k], v) for k, v in orc.st.items() if k.endswith(("running_mean", "running_var")))
     ep, ep_o = model.backbone_end_points, orc.end_points
@@ -115,8 +128,9 @@ def test_whole_model_matches_reference_gpu_path(cuda, ref_ext, task, la, over):
     # level while the bulk agrees to ~1e-6.  Hence norms for the bulk and a loose bound on the worst element.
     # Measured (profiles/RESULTS_r2.md): stage-1 features ~1e-6, logits 1e-4..3e-4, gradients ~1e-2 in the 2-norm.
     assert m["res1_l2"] <= 2e-5 and m["res2_l2"] <= 2e-4, m
-    assert m["res5_l2"] <= 5e-3 and m["logits_l2"] <= 2e-3 and m["logits_max"] <= 5e-2, m
-    assert m["dfeat_l2"] <= 5e-2 and m["dparam_l2"] <= 5e-2, m
+    assert m["res5_l2"] <= 2e-4 and m["logits_l2"] <= 2e-3 and m["logits_max"] <= 5e-2, m
+    assert m["dfeat_l2"] <= max(1e-4, 10 * m["ref_sens_dfeat_l2"]), m
+    assert m["dparam_l2"] <= max(1e-4, 10 * m["ref_sens_dparam_l2"]), m
     assert m["running_stats"] <= 1e-2, m
     # the loss of the task runs on the logits
     if task == "classification":

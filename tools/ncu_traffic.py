@@ -10,8 +10,12 @@ rows = list(csv.reader(out.splitlines()))
 h, units = rows[0], rows[1]
 ki, ri, wi, ti = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-MAP = [("sgemm", "cl3d_sgemm_algo"), ("gemm_tf32x3", "cl3d_sgemm_algo"), ("splitk_reduce", "cl3d_sgemm_algo"), ("ball_query", "cl3d_ball_query_algo"), ("grid_params", "cl3d_ball_query_algo"),
-       ("cell_", "cl3d_ball_query_algo"), ("zero_cells", "cl3d_ball_query_algo"), ("csr_", "cl3d_build_csr"),
+MAP = [("sgemm", "cl3d_sgemm_algo"), ("gemm_tf32x3", "cl3d_sgemm_algo"), ("splitk_reduce", "cl3d_sgemm_algo"),
+       # round 2: the search and the transposed lists are one entry point (cl3d_ball_query_csr)
+       ("ball_query", "cl3d_ball_query_csr"), ("grid_params", "cl3d_ball_query_csr"), ("grid_build_fused", "cl3d_ball_query_csr"),
+       ("cell_", "cl3d_ball_query_csr"), ("zero_cells", "cl3d_ball_query_csr"), ("csr_", "cl3d_ball_query_csr"),
+       ("pg2_kernel<0>", "cl3d_agg_fwd"), ("pg2_kernel<(bool)0>", "cl3d_agg_fwd"), ("pg2_kernel<1>", "cl3d_agg_bwd"),
+       ("pg2_kernel<(bool)1>", "cl3d_agg_bwd"),
        ("pwmlp_fwd_kernel", "cl3d_pwmlp_fwd_stats"), ("pwmlp_out", "cl3d_pwmlp_fwd_out"), ("pwmlp_bwd", "cl3d_pwmlp_bwd"),
        ("agg_fwd", "cl3d_agg_fwd"), ("sincos_fwd", "cl3d_agg_fwd"), ("agg_bwd", "cl3d_agg_bwd"), ("sincos_bwd", "cl3d_agg_bwd"),
        ("bn_relu_fwd", "cl3d_bn_relu_fwd"), ("bn_relu_bwd", "cl3d_bn_relu_bwd"), ("bn_reduce2", "cl3d_bn_relu_bwd"),
@@ -28,6 +32,7 @@ for r in rows[2:]:
 d = {e: {"dram_bytes_per_step": v[0] / steps, "kernels": v[1] / steps, "time_us_under_ncu": v[2] / steps}
      for e, v in acc.items()}
 d["_report"] = os.path.basename(rep)
+d["_total_dram_bytes_per_step"] = sum(v[0] for v in acc.values()) / steps
 if clouds is not None:
     d["_clouds_per_gpu"] = clouds
 print(json.dumps({cfg: d}, indent=1))
