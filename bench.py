@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling captures: keeps the run to 3 steps)")
     return ap.parse_args()
 
 
@@ -662,7 +663,7 @@ def main():
     res = device_leg(spec, B_local, rank, world, device, args.steps, args.warmup, use_graph=not args.no_graph,
                      sampler=sampler, want_profile=True, keep=True)
     clocks = sampler.stop()
-    e2e = e2e_leg(args, spec, res, rank, world, device)
+    e2e = None if args.no_e2e else e2e_leg(args, spec, res, rank, world, device)
 
     # ---- the other BASELINE configurations, device-timed the same way (per-GPU shard of the 8-GPU configs)
     extra = {}

@@ -735,7 +735,7 @@ __device__ __forceinline__ int pair_row_channel(int r, int p0, int pairs_per_cta
 }
 
 template <int PI>
-__global__ void __launch_bounds__(kAggWarps * 32, 2) sincos_fwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, 3) sincos_fwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p0 = blockIdx.y * 32 * PI;
@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) sincos_fwd_kernel(const Agg
 }
 
 template <int PI>
-__global__ void __launch_bounds__(kAggWarps * 32, 2) sincos_bwd_kernel(const AggArgs a) {
+__global__ void __launch_bounds__(kAggWarps * 32, 3) sincos_bwd_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p0 = blockIdx.y * 32 * PI;

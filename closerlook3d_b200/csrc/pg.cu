@@ -307,7 +307,10 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
           const int n = pg_stage(s_rec, s_ent, valid, dx, dy, dz, roff, s_kx, s_ky, s_kz, a.nkp, a.influence, a.inv_extent,
                                  row_bytes);
           __syncwarp();
-          pg_consume<BWD>(rows, rec_a, ent_a, wk_a, pacc_a, fown, owner, n, acc);
+          // Only the lanes that own channels walk the lists.  A shared-memory access is served per quarter warp: with
+          // all 32 lanes active (the spare ones shadowing lane 0) a 16-byte weight / accumulator access took 4
+          // wavefronts, with lanes 0..17 it takes 3 -- and this kernel is bound by exactly those wavefronts.
+          if (owner) pg_consume<BWD>(rows, rec_a, ent_a, wk_a, pacc_a, fown, true, n, acc);
           __syncwarp();
         }
       }

@@ -39,11 +39,25 @@ class _FusedAggBNReLU(Function):
         B, C, N = features.shape
         M = query_xyz.shape[1]
         feat_pm = ops.to_point_major(features)   # overlaps the neighbour search running on the side stream
-        nl.wait()
         training = bn.training or (bn.running_mean is None)
-        agg, partial = ops.agg_fwd(spec.family, spec.reduction, feat_pm, query_xyz, support_xyz, nl.idx, nl.ncount,
-                                   p0, p1, C, spec.radius, spec.normalize, spec.shared, spec.nkp, spec.extent,
-                                   spec.influence, want_bn_partial=training)
+        if nl.parts:
+            # the batch was searched in parts: aggregate part h as soon as ITS search is done, beside the search of h+1
+            L = ops._lib.lib()
+            agg = torch.empty(B, C, M, dtype=torch.float32, device=features.device)
+            tpc = L.cl3d_agg_num_tiles(1, M)      # BatchNorm partial rows per cloud
+            partial = torch.empty(B * tpc, 2, C, dtype=torch.float32, device=features.device) if training else None
+            cur = torch.cuda.current_stream()
+            for b0, b1, ev in nl.parts:
+                cur.wait_event(ev)
+                ops.agg_fwd(spec.family, spec.reduction, feat_pm[b0:b1], query_xyz[b0:b1], support_xyz[b0:b1],
+                            nl.idx[b0:b1], nl.ncount[b0:b1], p0, p1, C, spec.radius, spec.normalize, spec.shared,
+                            spec.nkp, spec.extent, spec.influence, want_bn_partial=training,
+                            out=(agg[b0:b1], partial[b0 * tpc:b1 * tpc] if training else None))
+        else:
+            nl.wait()
+            agg, partial = ops.agg_fwd(spec.family, spec.reduction, feat_pm, query_xyz, support_xyz, nl.idx, nl.ncount,
+                                       p0, p1, C, spec.radius, spec.normalize, spec.shared, spec.nkp, spec.extent,
+                                       spec.influence, want_bn_partial=training)
         momentum = bn.momentum if bn.momentum is not None else 0.0
         if training and bn.running_mean is not None:
             bn.num_batches_tracked.add_(1)

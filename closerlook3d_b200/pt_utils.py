@@ -42,6 +42,7 @@ class NeighborList:
         self.idx, self.ncount, self._idx_mask, self.N = idx, ncount, idx_mask, N
         self._csr = None
         self._csr_all = None
+        self.parts = None          # [(b0, b1, search-done event)] when the batch was searched in parts
         self.event = None
         self._csr_event = None
         self._csr_all_event = None
@@ -101,6 +102,10 @@ class NeighborList:
 
 _SIDE = {}
 overlap_enabled = True  # run the neighbour search on a side stream (fork/join), see NeighborList
+# Search the clouds of a batch in this many parts (clouds are independent).  The fused operators start the forward of
+# part 0 as soon as ITS search is done, so the issue-bound search of part 1 runs beside the L1-bound aggregation of
+# part 0 instead of in front of it.  1 = off.
+batch_parts = 1   # measured at c3 (profiles/RESULTS_r2.md): 2 parts 1.154 ms/step vs 1.107 -- half-batch kernels lose more to tail effects than the overlap wins
 
 
 def _side_stream(device, priority=0):
@@ -150,21 +155,44 @@ def neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
         cur = torch.cuda.current_stream()
         side = _side_stream(query_xyz.device)
         side.wait_stream(cur)
+        B = query_xyz.shape[0]
+        nparts = max(1, min(int(batch_parts), B)) if csr else 1   # parts only pay off when a fused forward follows
+        parts = None
         with torch.cuda.stream(side):
-            ev = torch.cuda.Event()          # search done: idx / ncount final (the forward kernels wait for this one)
-            res = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
-                                 want_mask=need_mask, want_ncount=True, csr=csr,
-                                 after_search=(lambda: ev.record(side)) if csr else None)
+            if nparts == 1:
+                ev = torch.cuda.Event()      # search done: idx / ncount final (the forward kernels wait for this one)
+                res = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
+                                     want_mask=need_mask, want_ncount=True, csr=csr,
+                                     after_search=(lambda: ev.record(side)) if csr else None)
+                if not csr:
+                    ev.record(side)
+                idx, idx_mask, ncount = res[:3]
+                lists = res[3] if csr else None
+            else:
+                M, N, K, dev = query_xyz.shape[1], support_xyz.shape[1], int(nsample), query_xyz.device
+                idx = torch.empty(B, M, K, dtype=torch.int32, device=dev)
+                idx_mask = torch.empty(B, M, K, dtype=torch.int32, device=dev) if need_mask else None
+                ncount = torch.empty(B, M, dtype=torch.int32, device=dev)
+                lists = (torch.empty(B, N + 1, dtype=torch.int32, device=dev),
+                         torch.empty(B, M * K, dtype=torch.int32, device=dev))
+                parts = []
+                for h in range(nparts):
+                    b0, b1 = (B * h) // nparts, (B * (h + 1)) // nparts
+                    evh = torch.cuda.Event()
+                    out = dict(idx=idx[b0:b1], idx_mask=idx_mask[b0:b1] if need_mask else None, ncount=ncount[b0:b1],
+                               off=lists[0][b0:b1], ent=lists[1][b0:b1])
+                    ops.ball_query(query_xyz[b0:b1], support_xyz[b0:b1], query_mask[b0:b1], support_mask[b0:b1], radius,
+                                   nsample, want_mask=need_mask, want_ncount=True, csr=csr, out=out,
+                                   after_search=(lambda e=evh: e.record(side)))
+                    parts.append((b0, b1, evh))
+                ev = parts[-1][2]            # every part searched (stream order)
             ev_lists = None
             if csr:                          # lists done: only the backward waits for this one
                 ev_lists = torch.cuda.Event()
                 ev_lists.record(side)
-            else:
-                ev.record(side)
-        idx, idx_mask, ncount = res[:3]
-        lists = res[3] if csr else None
         nl = NeighborList(idx, ncount, idx_mask, support_xyz.shape[1])
         nl.event = ev
+        nl.parts = parts
     else:
         res = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
                              want_mask=need_mask, want_ncount=True, csr=csr)

@@ -1,12 +1,15 @@
 #!/bin/bash
-# one `ncu --set full` report of ONE eager step per BASELINE config (run on the GPU box):  tools/capture_traffic.sh <tag>
-# skips the warm-up launches of bench.py (--steps 1 --warmup 0 --no-graph: first the launch-count step, then the timed
-# step, then the profile step: three identical steps; the report holds all three -> steps=3 in tools/ncu_traffic.py)
+# DRAM bytes + device time of every kernel of the steps of each BASELINE config (run on the GPU box):
+#   tools/capture_traffic.sh <tag>   ->  gpurun_out/<tag>_traffic_c{1..5}.csv   (a light ncu pass: three metrics, no
+# report file -- a full-metric capture of all kernels of all five configs took > 25 min and > 64 MB)
+# bench.py --steps 1 --warmup 0 --no-graph --no-e2e runs three identical eager steps (launch count, timed, profiled);
+# tools/ncu_traffic.py counts the steps from the once-per-step bn_finalize kernel anyway.
 TAG=$1
 mkdir -p gpurun_out
 for c in 1 2 3 4 5; do
-  timeout 900 ncu --set full --clock-control none -o gpurun_out/${TAG}_traffic_c$c -f \
-    python bench.py --config $c --steps 1 --warmup 0 --no-graph --no-extra-configs --no-cpu-baseline --no-ref-gpu \
+  timeout 400 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    --csv --log-file gpurun_out/${TAG}_traffic_c$c.csv \
+    python bench.py --config $c --steps 1 --warmup 0 --no-graph --no-extra-configs --no-cpu-baseline --no-ref-gpu --no-e2e \
     > gpurun_out/${TAG}_traffic_c$c.log 2>&1
-  tail -1 gpurun_out/${TAG}_traffic_c$c.log | cut -c1-200
+  grep -c "cl3d::" gpurun_out/${TAG}_traffic_c$c.csv
 done
