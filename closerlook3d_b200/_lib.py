@@ -43,9 +43,9 @@ SIGNATURES = {
     "cl3d_agg_num_params": (_i, [_i, _i, _i, _i]),
     "cl3d_agg_bwd_num_blocks": (_i, [_i, _i]),
     "cl3d_agg_fwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _i, _vp,
-                          _vp, _vp]),
+                          _vp, _vp, _vp]),
     "cl3d_agg_bwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f,
-                          _i, _vp, _vp, _vp]),
+                          _i, _vp, _vp, _vp, _vp]),
     "cl3d_reduce_partials": (_i, [_vp, _i, _i, _vp, _vp]),
     "cl3d_bn_finalize": (_i, [_vp, _i, _i, _ll, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "cl3d_bn_relu_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

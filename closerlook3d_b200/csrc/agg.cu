@@ -26,63 +26,6 @@
 
 namespace cl3d {
 
-// ---------------------------------------------------------------------------------------------
-// family weights
-// ---------------------------------------------------------------------------------------------
-template <int FAM, int CI>
-struct LaneParams {  // per-lane, per owned channel constants
-  int axis[CI];      // XYZ / SINCOS: which coordinate
-  float a[CI];       // SINCOS: dim_mat value ; ADAPTIVE: Wx
-  float b[CI];       // ADAPTIVE: Wy
-  float c[CI];       // ADAPTIVE: Wz
-  float d[CI];       // ADAPTIVE: bias
-  int is_cos[CI];
-};
-
-template <int FAM, int CI>
-__device__ __forceinline__ void load_lane_params(LaneParams<FAM, CI>& lp, const AggArgs& a, int c0, int lane) {
-#pragma unroll
-  for (int i = 0; i < CI; ++i) {
-    const int c = c0 + lane + 32 * i;
-    lp.axis[i] = 0;
-    lp.a[i] = 1.f;
-    lp.b[i] = lp.c[i] = lp.d[i] = 0.f;
-    lp.is_cos[i] = 0;
-    if (c >= a.C) continue;
-    if constexpr (FAM == CL3D_FAM_POSPOOL_XYZ) {
-      lp.axis[i] = c % 3;  // view(B, C//3, 3, ...) : local_aggregation_operators.py:67
-    } else if constexpr (FAM == CL3D_FAM_POSPOOL_SINCOS) {
-      const int F = a.C / 6;  // channel = axis*2F + t ; t<F sin, t>=F cos  (:70-83)
-      const int t = c % (2 * F);
-      lp.axis[i] = c / (2 * F);
-      lp.is_cos[i] = t >= F;
-      lp.a[i] = a.p0[t % F];
-    } else if constexpr (FAM == CL3D_FAM_ADAPTIVE_DP) {
-      const int g = c / a.shared;  // :194-197 channel c uses weight row c // S
-      lp.a[i] = a.p0[g * 3 + 0];
-      lp.b[i] = a.p0[g * 3 + 1];
-      lp.c[i] = a.p0[g * 3 + 2];
-      lp.d[i] = a.p1[g];
-    }
-  }
-}
-
-// weight of channel slot i for relative position dp (float4: x,y,z,-)
-template <int FAM, int CI>
-__device__ __forceinline__ float family_weight(const LaneParams<FAM, CI>& lp, int i, const float4& dp) {
-  if constexpr (FAM == CL3D_FAM_POSPOOL_XYZ) {
-    return lp.axis[i] == 0 ? dp.x : (lp.axis[i] == 1 ? dp.y : dp.z);
-  } else if constexpr (FAM == CL3D_FAM_POSPOOL_SINCOS) {
-    const float p = lp.axis[i] == 0 ? dp.x : (lp.axis[i] == 1 ? dp.y : dp.z);
-    const float arg = __fdiv_rn(__fmul_rn(100.f, p), lp.a[i]);  // torch.div(alpha * dp, dim_mat) :75-77
-    return lp.is_cos[i] ? cosf(arg) : sinf(arg);
-  } else if constexpr (FAM == CL3D_FAM_ADAPTIVE_DP) {
-    return fmaf(lp.c[i], dp.z, fmaf(lp.b[i], dp.y, fmaf(lp.a[i], dp.x, lp.d[i])));  // 1x1 conv 3 -> C/S, bias
-  } else {
-    return 0.f;
-  }
-}
-
 // PseudoGrid influence of kernel point kp on relative position dp (:385-403), mask applied by caller
 __device__ __forceinline__ float pg_influence(float dx, float dy, float dz, const float* kp, int influence,
                                               float inv_extent) {
@@ -998,8 +941,12 @@ extern "C" int cl3d_agg_num_params(int family, int C, int shared, int nkp) {
 
 static int check_common(int family, int reduction, int B, int N, int M, int K, int C, int shared, int nkp) {
   CL3D_REQUIRE(family >= 0 && family <= 3, "cl3d_agg: unknown family %d", family);
-  CL3D_REQUIRE(reduction == CL3D_REDUCE_AVG || reduction == CL3D_REDUCE_SUM,
-               "cl3d_agg: fused kernels implement avg / sum reductions (got %d)", reduction);
+  CL3D_REQUIRE(reduction == CL3D_REDUCE_AVG || reduction == CL3D_REDUCE_SUM || reduction == CL3D_REDUCE_MAX,
+               "cl3d_agg: unknown reduction %d", reduction);
+  if (reduction == CL3D_REDUCE_MAX) {
+    CL3D_REQUIRE(family != CL3D_FAM_PSEUDOGRID, "cl3d_agg: PseudoGrid sums over its neighbours (no max reduction)");
+    CL3D_REQUIRE(K <= 256, "cl3d_agg: max reduction stores the winning slot in one byte (nsample %d > 256)", K);
+  }
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 1 && K >= 1 && C >= 1, "cl3d_agg: bad sizes");
   if (family == CL3D_FAM_POSPOOL_XYZ) CL3D_REQUIRE(C % 3 == 0, "PosPool xyz needs C %% 3 == 0 (got %d)", C);
   if (family == CL3D_FAM_POSPOOL_SINCOS) CL3D_REQUIRE(C % 6 == 0, "PosPool sin_cos needs C %% 6 == 0 (got %d)", C);
@@ -1026,10 +973,11 @@ extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, con
                             const float* support_xyz, const int* idx, const int* ncount, const float* p0,
                             const float* p1, int B, int N, int M, int K, int C, float radius, int normalize,
                             int shared, int nkp, float extent, int influence, float* agg, float* bn_partial,
-                            cl3d_stream_t stream_) {
+                            unsigned char* arg_pm, cl3d_stream_t stream_) {
   int rc = check_common(family, reduction, B, N, M, K, C, shared, nkp);
   if (rc) return rc;
   CL3D_REQUIRE(feat_pm && query_xyz && support_xyz && idx && ncount && agg, "cl3d_agg_fwd: null pointer");
+  CL3D_REQUIRE(reduction != CL3D_REDUCE_MAX || arg_pm, "cl3d_agg_fwd: max reduction needs the arg_pm buffer");
   if (B == 0) return CL3D_OK;
   AggArgs a = {};
   a.feat_pm = feat_pm;
@@ -1043,6 +991,8 @@ extern "C" int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, con
   a.partial = bn_partial;
   fill_common(a, B, N, M, K, C, radius, reduction, normalize, shared, nkp, extent, influence);
   a.ntiles = B * ceil_div(M, kTile);
+  a.arg_pm = arg_pm;
+  if (reduction == CL3D_REDUCE_MAX) return aggmax_launch(family, a, false, a.ntiles, (cudaStream_t)stream_);
   if (family == CL3D_FAM_PSEUDOGRID && pg2_supported(a)) return pg2_launch_fwd(a, (cudaStream_t)stream_);
   return dispatch_fwd(family, pick_ci(family, a.Cp), a, (cudaStream_t)stream_);
 }
@@ -1051,13 +1001,15 @@ extern "C" int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const 
                             const float* query_xyz, const float* support_xyz, const int* ncount,
                             const int* csr_off, const int* csr_ent, const float* p0, const float* p1, int B, int N,
                             int M, int K, int C, float radius, int normalize, int shared, int nkp, float extent,
-                            int influence, float* grad_feat, float* grad_params_partial, cl3d_stream_t stream_) {
+                            int influence, float* grad_feat, float* grad_params_partial,
+                            const unsigned char* arg_pm, cl3d_stream_t stream_) {
   int rc = check_common(family, reduction, B, N, M, K, C, shared, nkp);
   if (rc) return rc;
   CL3D_REQUIRE(g_pm && query_xyz && support_xyz && ncount && csr_off && csr_ent && grad_feat,
                "cl3d_agg_bwd: null pointer");
   const bool has_params = family == CL3D_FAM_ADAPTIVE_DP || family == CL3D_FAM_PSEUDOGRID;
   CL3D_REQUIRE(!has_params || (feat_pm && grad_params_partial), "cl3d_agg_bwd: family needs feat_pm and a partial buffer");
+  CL3D_REQUIRE(reduction != CL3D_REDUCE_MAX || arg_pm, "cl3d_agg_bwd: max reduction needs the forward's arg_pm");
   if (B == 0) return CL3D_OK;
   AggArgs a = {};
   a.feat_pm = feat_pm;
@@ -1073,6 +1025,8 @@ extern "C" int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const 
   a.partial = grad_params_partial;
   fill_common(a, B, N, M, K, C, radius, reduction, normalize, shared, nkp, extent, influence);
   a.ntiles = B * ceil_div(N, kTile);
+  a.arg_pm = const_cast<unsigned char*>(arg_pm);
+  if (reduction == CL3D_REDUCE_MAX) return aggmax_launch(family, a, true, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);
   if (family == CL3D_FAM_PSEUDOGRID && pg2_supported(a))
     return pg2_launch_bwd(a, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);
   return dispatch_bwd(family, pick_ci(family, a.Cp), a, bwd_grid_x(a.ntiles), (cudaStream_t)stream_);

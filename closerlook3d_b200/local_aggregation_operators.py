@@ -8,7 +8,7 @@ MaskedQueryAndGroup + ~10 elementwise torch ops over (B,C,M,K) tensors:
     neighbour search (grid hash, cached)  ->  fused gather + transform + reduce  ->  fused BN + ReLU
 
 and each backward is a gather-form pass over transposed neighbour lists.  Settings no shipped cfg uses
-(output_conv, max reduction for the weight families, num_mlps > 1, ...) run through `_composed.py`, the same
+(output_conv, num_mlps > 1, gaussian influence, ...) run through `_composed.py`, the same
 mathematics on the materialising GPU kernels (still no CPU path).
 """
 import math
@@ -40,7 +40,11 @@ class _FusedAggBNReLU(Function):
         M = query_xyz.shape[1]
         feat_pm = ops.to_point_major(features)   # overlaps the neighbour search running on the side stream
         training = bn.training or (bn.running_mean is None)
+        arg = None
+        if spec.reduction == ops.REDUCE["max"]:   # winning slot per (query, channel), read again by the backward
+            arg = torch.empty(B, M, feat_pm.shape[2], dtype=torch.uint8, device=features.device)
         if nl.parts:
+            assert arg is None, "batch-parts search is an experiment for the sum / avg reductions"
             # the batch was searched in parts: aggregate part h as soon as ITS search is done, beside the search of h+1
             L = ops._lib.lib()
             agg = torch.empty(B, C, M, dtype=torch.float32, device=features.device)
@@ -57,7 +61,7 @@ class _FusedAggBNReLU(Function):
             nl.wait()
             agg, partial = ops.agg_fwd(spec.family, spec.reduction, feat_pm, query_xyz, support_xyz, nl.idx, nl.ncount,
                                        p0, p1, C, spec.radius, spec.normalize, spec.shared, spec.nkp, spec.extent,
-                                       spec.influence, want_bn_partial=training)
+                                       spec.influence, want_bn_partial=training, arg=arg)
         momentum = bn.momentum if bn.momentum is not None else 0.0
         if training and bn.running_mean is not None:
             bn.num_batches_tracked.add_(1)
@@ -70,19 +74,19 @@ class _FusedAggBNReLU(Function):
         ctx.spec, ctx.nl, ctx.training, ctx.N = spec, nl, training, N
         needs_feat = spec.family in (ops.FAM_ADAPTIVE_DP, ops.FAM_PSEUDOGRID)
         ctx.save_for_backward(agg, stats, bn_weight, bn_bias, query_xyz, support_xyz, p0, p1,
-                              feat_pm if needs_feat else None)
+                              feat_pm if needs_feat else None, arg)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        agg, stats, bn_weight, bn_bias, query_xyz, support_xyz, p0, p1, feat_pm = ctx.saved_tensors
+        agg, stats, bn_weight, bn_bias, query_xyz, support_xyz, p0, p1, feat_pm, arg = ctx.saved_tensors
         spec, nl = ctx.spec, ctx.nl
         C = agg.shape[1]
         g_pm, dgamma, dbeta = ops.bn_relu_bwd(grad_out.contiguous(), agg, stats, bn_weight, bn_bias, ctx.training)
         off, ent = nl.csr()
         grad_feat, pg = ops.agg_bwd(spec.family, spec.reduction, g_pm, feat_pm, query_xyz, support_xyz, nl.ncount,
                                     off, ent, p0, p1, C, ctx.N, spec.nsample, spec.radius, spec.normalize,
-                                    spec.shared, spec.nkp, spec.extent, spec.influence)
+                                    spec.shared, spec.nkp, spec.extent, spec.influence, arg=arg)
         gp0 = gp1 = None
         if spec.family == ops.FAM_ADAPTIVE_DP:  # pg: (4, C) rows x,y,z,bias per channel -> fold shared groups
             S = spec.shared
@@ -132,8 +136,8 @@ class PosPool(nn.Module):
         self._dim_mat = None
 
     def _fusable(self):
-        return (not self.output_conv) and self.reduction in ("avg", "mean", "sum") and \
-            self.position_embedding in ("xyz", "sin_cos")
+        return (not self.output_conv) and self.position_embedding in ("xyz", "sin_cos") and \
+            (self.reduction in ("avg", "mean", "sum") or (self.reduction == "max" and self.nsample <= 256))
 
     def forward(self, query_xyz, support_xyz, query_mask, support_mask, support_features):
         """(B,M,3),(B,N,3),(B,M) i32,(B,N) i32,(B,C,N) -> (B,C_out,M)   (reference :47-112)"""
@@ -193,7 +197,8 @@ class AdaptiveWeight(nn.Module):
         _out_block(self, in_channels, out_channels, config.bn_momentum)
 
     def _fusable(self):
-        return (not self.output_conv) and self.num_mlps == 1 and self.reduction in ("avg", "mean", "sum")
+        return (not self.output_conv) and self.num_mlps == 1 and \
+            (self.reduction in ("avg", "mean", "sum") or (self.reduction == "max" and self.nsample <= 256))
 
     def forward(self, query_xyz, support_xyz, query_mask, support_mask, support_features):
         """reference :170-224"""

@@ -184,8 +184,9 @@ REDUCE = {"avg": 0, "mean": 0, "sum": 1, "max": 2}
 
 @_on_device
 def agg_fwd(family, reduction, feat_pm, query_xyz, support_xyz, idx, ncount, p0, p1, C, radius, normalize, shared=1,
-            nkp=0, extent=1.0, influence=0, want_bn_partial=True, out=None):
-    """-> (agg (B,C,M), bn_partial (ntiles,2,C) | None); out = (agg, partial) preallocated (e.g. batch slices)"""
+            nkp=0, extent=1.0, influence=0, want_bn_partial=True, out=None, arg=None):
+    """-> (agg (B,C,M), bn_partial (ntiles,2,C) | None); out = (agg, partial) preallocated (e.g. batch slices);
+    arg = (B,M,Cp) uint8 buffer for the winning slots, required by (and only by) the max reduction"""
     B, N, Cp = feat_pm.shape
     M, K = idx.shape[1], idx.shape[2]
     L = _lib.lib()
@@ -197,14 +198,15 @@ def agg_fwd(family, reduction, feat_pm, query_xyz, support_xyz, idx, ncount, p0,
         partial = torch.empty(L.cl3d_agg_num_tiles(B, M), 2, C, dtype=F32, device=dev) if want_bn_partial else None
     check(L.cl3d_agg_fwd(family, reduction, ptr(feat_pm), ptr(query_xyz), ptr(support_xyz), ptr(idx), ptr(ncount),
                          ptr(p0), ptr(p1), B, N, M, K, C, float(radius), int(normalize), int(shared), int(nkp),
-                         float(extent), int(influence), ptr(agg), ptr(partial), stream_ptr()), "cl3d_agg_fwd")
+                         float(extent), int(influence), ptr(agg), ptr(partial), ptr(arg), stream_ptr()), "cl3d_agg_fwd")
     return agg, partial
 
 
 @_on_device
 def agg_bwd(family, reduction, g_pm, feat_pm, query_xyz, support_xyz, ncount, csr_off, csr_ent, p0, p1, C, N, K,
-            radius, normalize, shared=1, nkp=0, extent=1.0, influence=0):
-    """-> (grad_feat (B,C,N), param_grad (P//C, C) | None)   P = 4C (adaptive: x,y,z,bias) or nkp*C"""
+            radius, normalize, shared=1, nkp=0, extent=1.0, influence=0, arg=None):
+    """-> (grad_feat (B,C,N), param_grad (P//C, C) | None)   P = 4C (adaptive: x,y,z,bias) or nkp*C;
+    arg = the forward's winning slots (max reduction)"""
     B, M, Cp = g_pm.shape
     L = _lib.lib()
     dev = g_pm.device
@@ -216,7 +218,7 @@ def agg_bwd(family, reduction, g_pm, feat_pm, query_xyz, support_xyz, ncount, cs
     check(L.cl3d_agg_bwd(family, reduction, ptr(g_pm), ptr(feat_pm), ptr(query_xyz), ptr(support_xyz), ptr(ncount),
                          ptr(csr_off), ptr(csr_ent), ptr(p0), ptr(p1), B, N, M, K, C, float(radius), int(normalize),
                          int(shared), int(nkp), float(extent), int(influence), ptr(grad_feat), ptr(partial),
-                         stream_ptr()), "cl3d_agg_bwd")
+                         ptr(arg), stream_ptr()), "cl3d_agg_bwd")
     pg = reduce_partials(partial).view(P // C, C) if P > 0 else None
     return grad_feat, pg
 

@@ -171,7 +171,10 @@ int cl3d_to_channel_major(const float* in_nc, int B, int C, int N, float* out_cn
  *               cl3d_agg_bwd_num_blocks(B,N), P = cl3d_agg_num_params(...) laid out (slot, C) with
  *               slot = {x,y,z,bias} (ADAPTIVE_DP, per channel: the caller folds `shared` groups) or the
  *               kernel point (PSEUDOGRID); reduce with cl3d_reduce_partials.
- * Only avg / sum reductions are fused (every shipped cfg uses avg; PseudoGrid is sum by construction).
+ * reduction = CL3D_REDUCE_MAX (PosPool, AdaptiveWeight; local_aggregation_operators.py:87-91,199-203 --
+ *   F.max_pool2d over nsample and its autograd backward): arg_pm (B,M,Cp) bytes receives the winning slot of
+ *   every (query, channel) in the forward and is read by the backward; nsample <= 256.  Pass NULL for avg / sum.
+ *   PseudoGrid is a sum by construction (CL3D_ERR_BAD_ARG for max).
  * ---------------------------------------------------------------------------------------------- */
 int cl3d_agg_num_tiles(int B, int M);
 int cl3d_agg_bwd_num_blocks(int B, int N);
@@ -180,12 +183,13 @@ int cl3d_agg_fwd(int family, int reduction, const float* feat_pm, const float* q
                  const float* support_xyz, const int* idx, const int* ncount, const float* p0,
                  const float* p1, int B, int N, int M, int K, int C, float radius, int normalize,
                  int shared, int nkp, float extent, int influence, float* agg, float* bn_partial,
-                 cl3d_stream_t stream);
+                 unsigned char* arg_pm, cl3d_stream_t stream);
 int cl3d_agg_bwd(int family, int reduction, const float* g_pm, const float* feat_pm,
                  const float* query_xyz, const float* support_xyz, const int* ncount,
                  const int* csr_off, const int* csr_ent, const float* p0, const float* p1, int B, int N,
                  int M, int K, int C, float radius, int normalize, int shared, int nkp, float extent,
-                 int influence, float* grad_feat, float* grad_params_partial, cl3d_stream_t stream);
+                 int influence, float* grad_feat, float* grad_params_partial,
+                 const unsigned char* arg_pm, cl3d_stream_t stream);
 /* out[p] = sum_t partial[t][p]  (fixed order -> deterministic given the partials) */
 int cl3d_reduce_partials(const float* partial, int ntiles, int P, float* out, cl3d_stream_t stream);
 

@@ -63,7 +63,7 @@ DIM_MAT_FN = None
 KEEP = None
 
 
-def argmax_is_decided(premax, idx, rel=2e-5):
+def argmax_is_decided(premax, idx, rel=2e-5, relu=True):
     """(B,C,M) bool: the largest activation over K beats the best activation of any OTHER neighbour by more than
     rel * max(1, |value|).  Duplicated slots of the same neighbour (cyclic padding) do not count as competitors:
     routing the gradient to either copy is the same gradient; neither does a maximum of 0 (ReLU output)."""
@@ -72,8 +72,9 @@ def argmax_is_decided(premax, idx, rel=2e-5):
     other = ig != ig[..., :1]
     second = torch.where(other, xs, torch.full_like(xs, float("-inf"))).max(-1)[0]
     v1 = xs[..., 0]
-    # the activations are post-ReLU: a maximum of exactly 0 passes no gradient whichever slot holds it
-    return ((v1 - second) > rel * v1.abs().clamp(min=1.0)) | (v1 <= 0)
+    clear = (v1 - second) > rel * v1.abs().clamp(min=1.0)
+    # post-ReLU activations (PointWiseMLP): a maximum of exactly 0 passes no gradient whichever slot holds it
+    return (clear | (v1 <= 0)) if relu else clear
 
 
 def query_and_group(ext, query_xyz, support_xyz, query_mask, support_mask, features, radius, nsample,
@@ -94,6 +95,8 @@ def query_and_group(ext, query_xyz, support_xyz, query_mask, support_mask, featu
         else:
             grouped_xyz = grouped_xyz / radius                                # :128-129 true division by float(radius)
     grouped_features = group(features, idx) if features is not None else None
+    if KEEP is not None:
+        KEEP["idx"] = idx.long()
     return grouped_features, grouped_xyz, idx_mask, idx
 
 
@@ -132,6 +135,8 @@ def _feature_mask(idx_mask, query_mask):
 def _reduce(agg, idx_mask, query_mask, reduction):
     """local_aggregation_operators.py:87-105 (identical in all families). agg (B,C,M,K) -> (B,C,M)"""
     if reduction == "max":
+        if KEEP is not None:
+            KEEP["premax"] = agg.detach()
         return agg.max(dim=-1)[0]
     fm = _feature_mask(idx_mask, query_mask)[:, None, :, :]
     agg = agg * fm

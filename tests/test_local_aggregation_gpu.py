@@ -77,14 +77,19 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
     orc.training = train
     od = oracle_device
     f_ref = feats.clone().to(od).requires_grad_(True)
-    la_oracle.KEEP = {} if (la_type == "pointwisemlp" and over["pointwisemlp"].get("reduction") == "max") else None
+    is_max = over.get(la_type, {}).get("reduction") == "max" and la_type != "pseudo_grid"
+    la_oracle.KEEP = {} if is_max else None
     o_ref = orc(q.to(od), xyz.to(od), qm.to(od), mask.to(od), f_ref)
     decided = None
     if la_oracle.KEEP:
         # max over K: where the two best DISTINCT neighbours tie within the tolerance, rounding decides which one
         # receives the gradient (a discontinuity like the ReLU's); those (query, channel) positions get no
         # upstream gradient on either side
-        decided = la_oracle.argmax_is_decided(la_oracle.KEEP["pwmlp_premax"], la_oracle.KEEP["idx"]).cpu()
+        if la_type == "pointwisemlp":     # post-ReLU activations through the 3xTF32 GEMM
+            decided = la_oracle.argmax_is_decided(la_oracle.KEEP["pwmlp_premax"], la_oracle.KEEP["idx"]).cpu()
+        else:                             # products of fp32 inputs: the two sides differ at rounding level only
+            decided = la_oracle.argmax_is_decided(la_oracle.KEEP["premax"], la_oracle.KEEP["idx"], rel=2e-6,
+                                                  relu=False).cpu()
         assert int((~decided).sum()) <= max(4, decided.numel() // 2000), f"{int((~decided).sum())} undecided maxima"
     la_oracle.KEEP = None
     mod = mod.to(cuda)
@@ -126,6 +131,9 @@ def run_case(cuda, oracle_ext, la_type, over, B, N, K, C, seed, M=None, radius=N
 
 
 PW = dict(pointwisemlp=dict(feature_type="dp_fi_df", num_mlps=1, reduction="max"))
+XYZ_MAX = dict(pospool=dict(position_embedding="xyz", reduction="max"))
+SINCOS_MAX = dict(pospool=dict(position_embedding="sin_cos", reduction="max"))
+AW_MAX = dict(adaptive_weight=dict(weight_type="dp", num_mlps=1, shared_channels=1, reduction="max"))
 XYZ_AVG = dict(pospool=dict(position_embedding="xyz", reduction="avg"))
 SINCOS_AVG = dict(pospool=dict(position_embedding="sin_cos", reduction="avg"))
 AW = dict(adaptive_weight=dict(weight_type="dp", num_mlps=1, shared_channels=1, reduction="avg"))
@@ -145,6 +153,11 @@ AW = dict(adaptive_weight=dict(weight_type="dp", num_mlps=1, shared_channels=1, 
     ("pseudo_grid", dict(), 2, 3000, 26, 72),             # c3 operator shape, smaller cloud
     ("pseudo_grid", dict(pseudo_grid=dict(KP_influence="constant")), 2, 800, 16, 36),
     ("pseudo_grid", dict(), 2, 1500, 16, 144),            # two channel chunks
+    ("pospool", XYZ_MAX, 2, 1024, 16, 66),                # fused max reduction (agg_max.cu)
+    ("pospool", XYZ_MAX, 2, 1500, 40, 288),               # K > 32 (two rounds), three channel chunks
+    ("pospool", SINCOS_MAX, 2, 1024, 16, 66),
+    ("adaptive_weight", AW_MAX, 3, 1024, 16, 72),
+    ("adaptive_weight", dict(adaptive_weight=dict(shared_channels=4, reduction="max")), 2, 900, 20, 72),
     ("pointwisemlp", PW, 2, 1024, 16, 66),
     ("pointwisemlp", PW, 4, 1024, 32, 72),                # c2 operator shape, smaller batch
     ("pointwisemlp", PW, 2, 2500, 20, 36),

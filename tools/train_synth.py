@@ -49,6 +49,9 @@ def main():
     ap.add_argument("--points", type=int, default=None, help="points per cloud (default 10000 / 15000)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ddp", action="store_true",
+                    help="torch DistributedDataParallel (the reference's wrapper) instead of this package's flat "
+                         "gradient buffer + one all-reduce per step (closerlook3d_b200/dist.py)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -70,9 +73,14 @@ def main():
     model.init_weights()
     model = model.to(device).train()
     opt = torch.optim.SGD(model.parameters(), lr=B * world / 16 * 0.002, momentum=0.98, weight_decay=0.001)
-    net = model
-    if world > 1:
+    net, flat = model, None
+    if world > 1 and args.ddp:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
+    elif world > 1:
+        from closerlook3d_b200.dist import FlatGradients
+        for p in model.parameters():            # same start on every rank, as DDP's constructor does
+            dist.broadcast(p.data, 0)
+        flat = FlatGradients(model.parameters()).attach()
     batches = [synth_batch(B, N, cfg.input_features_dim, 100 * rank + i, device, scale) for i in range(3)]
     if args.task == "classification":
         targets = [torch.randint(0, cfg.num_classes, (B,), device=device) for _ in batches]
@@ -84,8 +92,13 @@ def main():
         pred = net(xyz, mask, feats)
         loss = criterion(pred, targets[i % len(batches)]) if args.task == "classification" else \
             criterion(pred, targets[i % len(batches)], mask.float())
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
+        if flat is not None:
+            flat.zero()                 # the gradients are views of one buffer: one memset, one all-reduce
+            loss.backward()
+            flat.allreduce()
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
         opt.step()
         return loss
 
@@ -120,7 +133,8 @@ def main():
                           "points_per_s": B * N * world / (float(ms.item()) * 1e-3), "loss": float(loss.item()),
                           "neighbour_cache_per_step": {k: v / args.steps for k, v in pt_utils.cache_stats.items()},
                           "params_M": sum(p.numel() for p in model.parameters()) / 1e6,
-                          "checkpoint_round_trip": ok, "launch": "eager (no CUDA graph), DDP broadcast_buffers=False"}))
+                          "checkpoint_round_trip": ok, "launch": "eager (no CUDA graph); " + ("DDP broadcast_buffers=False" if args.ddp or world == 1 else
+                                                                   "flat gradient buffer, one all-reduce per step")}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
