@@ -28,7 +28,8 @@ SIGNATURES = {
     "cl3d_ball_query_algo": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "cl3d_ball_query_csr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cl3d_ball_query_csr": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _i, _vp]),
-    "cl3d_nearest_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "cl3d_nearest_query_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cl3d_nearest_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cl3d_csr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cl3d_build_csr": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cl3d_group_points": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -811,6 +811,89 @@ __global__ void __launch_bounds__(256) nearest_query_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// nearest query over the cell grid (clouds too large for the tile scan above): thread per query, the supports'
+// cells visited in Chebyshev rings around the query's cell.  A point outside the (2r+1)^3 block is at least as far
+// as the block's nearest face that is not the grid's own boundary, so the walk stops as soon as the best distance
+// is below that bound; ties go to the smaller index, which is the reference's first strict minimum in index order
+// (masked_nearest_query_gpu.cu:37-52), and its start value min_dist = 100 is kept (:35).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nn_scan(const float4* __restrict__ sorted, int s, int e, float qx, float qy, float qz,
+                                        float& best_d, int& best_i) {
+  for (int t = s; t < e; ++t) {
+    const float4 p = sorted[t];
+    const float d2 = ref_d2(qx, qy, qz, p.x, p.y, p.z);
+    const int i = __float_as_int(p.w);
+    if (d2 < best_d || (d2 == best_d && i < best_i)) {
+      best_d = d2;
+      best_i = i;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nearest_query_grid_kernel(const float* __restrict__ query_xyz,
+                                                                 const int* __restrict__ query_mask,
+                                                                 const GridParams* __restrict__ params,
+                                                                 const int* __restrict__ cell_start,
+                                                                 const float4* __restrict__ sorted, int N, int M,
+                                                                 int cell_cap, int* __restrict__ idx,
+                                                                 int* __restrict__ idx_mask) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= M) return;
+  const GridParams p = params[b];
+  const int* cs = cell_start + (size_t)b * (cell_cap + 1);
+  const float4* pts = sorted + (size_t)b * N;
+  const float* qp = query_xyz + ((size_t)b * M + q) * 3;
+  const float qx = qp[0], qy = qp[1], qz = qp[2];
+  float best_d = 100.f;
+  int best_i = -1;
+  if (p.n_valid > 0) {
+    const float h = 1.0f / p.inv_h;
+    const int cx = cell_coord(qx, p.ox, p.inv_h, p.gx), cy = cell_coord(qy, p.oy, p.inv_h, p.gy),
+              cz = cell_coord(qz, p.oz, p.inv_h, p.gz);
+    const int rmax = max(max(max(cx, p.gx - 1 - cx), max(cy, p.gy - 1 - cy)), max(cz, p.gz - 1 - cz));
+    for (int r = 0; r <= rmax; ++r) {
+      const int x0 = max(cx - r, 0), x1 = min(cx + r, p.gx - 1);
+      const int y0 = max(cy - r, 0), y1 = min(cy + r, p.gy - 1);
+      const int z0 = max(cz - r, 0), z1 = min(cz + r, p.gz - 1);
+      for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+          const int base = p.gx * (y + p.gy * z);
+          if (z - cz == r || cz - z == r || y - cy == r || cy - y == r) {
+            // a row of the ring's shell: its cells are consecutive in the cell-sorted array
+            nn_scan(pts, cs[base + x0], cs[base + x1 + 1], qx, qy, qz, best_d, best_i);
+          } else {  // inner row: only the two end cells belong to ring r
+            if (cx - r >= 0) nn_scan(pts, cs[base + cx - r], cs[base + cx - r + 1], qx, qy, qz, best_d, best_i);
+            if (cx + r <= p.gx - 1) nn_scan(pts, cs[base + cx + r], cs[base + cx + r + 1], qx, qy, qz, best_d, best_i);
+          }
+        }
+      // lower bound of the distance to any point outside the block; a face on the grid's boundary has nothing
+      // behind it.  The margin covers the fp32 rounding of the cell coordinates (points) and of the faces.
+      float bound = 3.0e38f;
+      const float qa[3] = {qx, qy, qz}, oa[3] = {p.ox, p.oy, p.oz};
+      const int ca[3] = {cx, cy, cz}, ga[3] = {p.gx, p.gy, p.gz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (ca[a] - r > 0) {
+          const float face = oa[a] + (float)(ca[a] - r) * h;
+          bound = fminf(bound, (qa[a] - face) - (0.01f * h + 2e-6f * (fabsf(qa[a]) + fabsf(face))));
+        }
+        if (ca[a] + r < ga[a] - 1) {
+          const float face = oa[a] + (float)(ca[a] + r + 1) * h;
+          bound = fminf(bound, (face - qa[a]) - (0.01f * h + 2e-6f * (fabsf(qa[a]) + fabsf(face))));
+        }
+      }
+      if (bound > 0.f) {
+        if (best_i >= 0 && sqrtf(best_d) < bound) break;  // nothing outside can be nearer or tie
+        if (bound > 10.01f) break;                        // nothing outside can beat the start value 100
+      }
+    }
+  }
+  idx[(size_t)b * M + q] = best_i;
+  idx_mask[(size_t)b * M + q] = query_mask[(size_t)b * M + q] == 0 ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // CSR ("who gathers me") build: count -> scan -> fill
 // ---------------------------------------------------------------------------------------------
 __global__ void csr_count_kernel(const int* __restrict__ idx, const int* __restrict__ ncount, int N, int M, int K,
@@ -1035,17 +1118,50 @@ static int ball_query_impl(const float* query_xyz, const float* support_xyz, con
   return check_launch("ball_query_grid_kernel");
 }
 
+extern "C" size_t cl3d_nearest_query_workspace_bytes(int B, int N, int M) {
+  if (N <= kBruteMaxN) return 0;  // the tile scan needs none
+  return cl3d_ball_query_workspace_bytes(B, N, M, 1);
+}
+
 extern "C" int cl3d_nearest_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
                                   const int* support_mask, int B, int N, int M, int* idx, int* idx_mask,
-                                  cl3d_stream_t stream_) {
+                                  void* workspace, size_t workspace_bytes, cl3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   CL3D_REQUIRE(B >= 0 && N >= 1 && M >= 0, "cl3d_nearest_query: bad sizes");
   CL3D_REQUIRE(query_xyz && support_xyz && query_mask && support_mask && idx && idx_mask,
                "cl3d_nearest_query: null pointer");
   if (B == 0 || M == 0) return CL3D_OK;
-  nearest_query_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, stream>>>(query_xyz, support_xyz, query_mask, support_mask,
-                                                                      N, M, idx, idx_mask); CL3D_LAUNCHED(1);
-  return check_launch("nearest_query_kernel");
+  const bool grid = N > kBruteMaxN && workspace && !getenv("CL3D_NN_BRUTE");
+  if (!grid) {  // every support against every query, tiles in shared memory
+    nearest_query_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, stream>>>(query_xyz, support_xyz, query_mask,
+                                                                        support_mask, N, M, idx, idx_mask); CL3D_LAUNCHED(1);
+    return check_launch("nearest_query_kernel");
+  }
+  if (workspace_bytes < cl3d_nearest_query_workspace_bytes(B, N, M)) {
+    set_error("cl3d_nearest_query: workspace too small (%zu < %zu)", workspace_bytes,
+              cl3d_nearest_query_workspace_bytes(B, N, M));
+    return CL3D_ERR_WORKSPACE;
+  }
+  const int cap = cell_cap_for(N);
+  unsigned char* w = (unsigned char*)workspace;
+  GridParams* params = (GridParams*)w;
+  w += align_up(sizeof(GridParams) * (size_t)B, 256);
+  int* cell_cnt = (int*)w;
+  w += align_up(sizeof(int) * (size_t)B * cap, 256);
+  int* cell_start = (int*)w;
+  w += align_up(sizeof(int) * (size_t)B * (cap + 1), 256);
+  int2* cell_rank = (int2*)w;
+  w += align_up(sizeof(int2) * (size_t)B * N, 256);
+  float4* sorted = (float4*)w;
+  // no radius here: the build picks the smallest cell edge whose grid fits the cell budget (4 cells per point)
+  static std::atomic<unsigned long long> attr_build{0};
+  allow_big_smem(grid_build_fused_kernel, attr_build);
+  grid_build_fused_kernel<<<B, 1024, kFusedGridCells * sizeof(int), stream>>>(support_xyz, support_mask, N, 0.f, cap,
+                                                                              params, cell_cnt, cell_start, cell_rank,
+                                                                              sorted); CL3D_LAUNCHED(1);
+  nearest_query_grid_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, stream>>>(query_xyz, query_mask, params, cell_start,
+                                                                           sorted, N, M, cap, idx, idx_mask); CL3D_LAUNCHED(1);
+  return check_launch("nearest_query_grid_kernel");
 }
 
 extern "C" size_t cl3d_csr_workspace_bytes(int B, int N, int M, int K) {

@@ -103,8 +103,11 @@ def nearest_query(query_xyz, support_xyz, query_mask, support_mask):
     N = support_xyz.shape[1]
     idx = torch.empty(B, M, dtype=I32, device=query_xyz.device)
     idx_mask = torch.empty(B, M, dtype=I32, device=query_xyz.device)
-    check(_lib.lib().cl3d_nearest_query(ptr(query_xyz), ptr(support_xyz), ptr(query_mask), ptr(support_mask), B, N, M,
-                                        ptr(idx), ptr(idx_mask), stream_ptr()), "cl3d_nearest_query")
+    L = _lib.lib()
+    wsb = L.cl3d_nearest_query_workspace_bytes(B, N, M)      # 0: small cloud, tile scan; else the cell grid
+    ws = torch.empty(wsb, dtype=torch.uint8, device=query_xyz.device) if wsb else None
+    check(L.cl3d_nearest_query(ptr(query_xyz), ptr(support_xyz), ptr(query_mask), ptr(support_mask), B, N, M,
+                               ptr(idx), ptr(idx_mask), ptr(ws), wsb, stream_ptr()), "cl3d_nearest_query")
     return idx, idx_mask
 
 

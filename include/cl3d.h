@@ -90,10 +90,16 @@ int cl3d_ball_query_algo(const float* query_xyz, const float* support_xyz, const
                          int* idx_mask, int* ncount, void* workspace, size_t workspace_bytes, int algo,
                          cl3d_stream_t stream);
 
-/* Replaces _ext.masked_nearest_query (masked_nearest_query_gpu.cu:8-62). idx, idx_mask: (B,M) int32. */
+/* Replaces _ext.masked_nearest_query (masked_nearest_query_gpu.cu:8-62). idx, idx_mask: (B,M) int32.
+ * N <= 2048: every support against every query from shared-memory tiles.  Larger clouds: the supports are binned
+ * into the cell grid of the ball query (cell edge chosen from the cell budget) and each query walks rings of cells
+ * until nothing outside can be nearer; same result bit for bit, including the reference's tie rule (first minimum
+ * in index order) and its start value min_dist = 100.  workspace: cl3d_nearest_query_workspace_bytes (0 for small
+ * clouds); workspace == NULL always takes the tile scan. */
+size_t cl3d_nearest_query_workspace_bytes(int B, int N, int M);
 int cl3d_nearest_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
                        const int* support_mask, int B, int N, int M, int* idx, int* idx_mask,
-                       cl3d_stream_t stream);
+                       void* workspace, size_t workspace_bytes, cl3d_stream_t stream);
 
 /* Search AND transposed lists in one call (what a forward that will be differentiated needs): every counted slot
  * takes its rank inside its support point's list during the search's emit phase (int atomics), so the list build is

@@ -104,6 +104,35 @@ def test_nearest_query_bit_exact(cuda, oracle_ext, B, N, M):
     assert torch.equal(idx_mask.cpu(), ref_mask[..., 0])
 
 
+@pytest.mark.parametrize("offset,spread", [(0.0, 1.0), (25.0, 1.0), (0.0, 3.0)])
+def test_nearest_query_grid_surface_cloud(cuda, oracle_ext, offset, spread):
+    # the cell-ring walk (N > 2048) on surface-like supports (most cells empty: several rings per query), queries
+    # well outside the supports' bounding box (spread 3), S3DIS-like coordinates far from the origin (offset 25),
+    # exact duplicates among the supports (distance ties -> first index), masked tail, and against the tile scan
+    from closerlook3d_b200 import ops
+    B, N, M = 2, 6000, 9000
+    g = torch.Generator().manual_seed(5)
+    d = torch.randn(B, N, 3, generator=g)
+    xyz = d / d.norm(dim=-1, keepdim=True) * (0.5 + 0.01 * torch.randn(B, N, 1, generator=g)) + offset
+    xyz[:, 100:200] = xyz[:, 300:400]                      # duplicated points
+    mask = torch.ones(B, N, dtype=torch.int32)
+    mask[1, N - 500:] = 0
+    q = (torch.rand(B, M, 3, generator=g) - 0.5) * 1.2 * spread + offset
+    q[:, :300] = xyz[:, 100:400]                           # queries ON support points (distance 0, tied duplicates)
+    qm = torch.ones(B, M, dtype=torch.int32)
+    ref_idx, ref_mask = oracle_ext.masked_nearest_query(q, xyz.contiguous(), qm, mask)
+    idx, idx_mask = ops.nearest_query(q.to(cuda), xyz.contiguous().to(cuda), qm.to(cuda), mask.to(cuda))
+    assert torch.equal(idx.cpu(), ref_idx[..., 0])
+    assert torch.equal(idx_mask.cpu(), ref_mask[..., 0])
+    import os
+    os.environ["CL3D_NN_BRUTE"] = "1"
+    try:
+        idx2, _ = ops.nearest_query(q.to(cuda), xyz.contiguous().to(cuda), qm.to(cuda), mask.to(cuda))
+    finally:
+        del os.environ["CL3D_NN_BRUTE"]
+    assert torch.equal(idx2, idx)
+
+
 def test_csr_is_transpose_of_idx(cuda, oracle_ext):
     from closerlook3d_b200 import ops
     B, N, K = 3, 2500, 16

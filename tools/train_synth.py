@@ -47,7 +47,7 @@ def main():
     ap.add_argument("--la", default="pseudo_grid", choices=sorted(LA))
     ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default: the cfg's batch_size: 16 / 8)")
     ap.add_argument("--points", type=int, default=None, help="points per cloud (default 10000 / 15000)")
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ddp", action="store_true",
                     help="torch DistributedDataParallel (the reference's wrapper) instead of this package's flat "
@@ -108,15 +108,20 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    # one event per step boundary: mean AND median (a one-off stall -- allocator growth, a late NCCL channel set-up,
+    # python GC -- moved the 10-step mean of an 8-GPU run by 2x); every statistic is the max over ranks
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
     for i in range(args.steps):
         loss = step(args.warmup + i)
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    ms = torch.tensor([evs[0].elapsed_time(evs[-1]) / args.steps, per[len(per) // 2], per[-1]], device=device,
+                      dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_mean, ms_median, ms_worst = (float(v) for v in ms.tolist())
     # checkpoint round trip in the reference's format (train_modelnet_dist.py:152-160: {'model': state_dict, ...})
     ok = None
     if rank == 0:
@@ -129,8 +134,10 @@ def main():
         ok = all(torch.equal(a.cpu(), b) for a, b in zip(model.state_dict().values(), fresh.state_dict().values()))
         print(json.dumps({"what": "whole-model training step (fwd + loss + bwd + SGD), synthetic clouds",
                           "task": args.task, "local_aggregation": args.la, "n_gpus": world, "clouds_per_gpu": B,
-                          "points_per_cloud": N, "ms_per_step": float(ms.item()),
-                          "points_per_s": B * N * world / (float(ms.item()) * 1e-3), "loss": float(loss.item()),
+                          "points_per_cloud": N, "steps": args.steps, "ms_per_step": ms_mean,
+                          "ms_per_step_median": ms_median, "ms_slowest_step": ms_worst,
+                          "points_per_s": B * N * world / (ms_mean * 1e-3),
+                          "points_per_s_median_step": B * N * world / (ms_median * 1e-3), "loss": float(loss.item()),
                           "neighbour_cache_per_step": {k: v / args.steps for k, v in pt_utils.cache_stats.items()},
                           "params_M": sum(p.numel() for p in model.parameters()) / 1e6,
                           "checkpoint_round_trip": ok, "launch": "eager (no CUDA graph); " + ("DDP broadcast_buffers=False" if args.ddp or world == 1 else
