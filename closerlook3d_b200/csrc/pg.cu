@@ -203,8 +203,14 @@ __device__ __forceinline__ void pg_consume(const float* __restrict__ rows, uint3
   }
 }
 
-// kernel points (p0: (nkp,3)) and kernel weights (p1: (nkp,C)) -> shared memory
-__device__ __forceinline__ void pg_load_params(const AggArgs& a, const PgSmem& L, unsigned char* smem) {
+// Layers wider than 128 channels run as gridDim.y channel chunks of equal width (a multiple of 4, <= 128): every
+// chunk stages the influences again -- as the first generation does per 96 channels -- but keeps this kernel's
+// cheaper pair loop.
+__host__ __device__ inline int pg_num_chunks(int Cp) { return (Cp + 127) / 128; }
+__host__ __device__ inline int pg_chunk_width(int Cp, int nchunks) { return ((Cp + nchunks - 1) / nchunks + 3) / 4 * 4; }
+
+// kernel points (p0: (nkp,3)) and kernel weights (p1: (nkp,C), channels c0 .. c0+CpR) -> shared memory
+__device__ __forceinline__ void pg_load_params(const AggArgs& a, const PgSmem& L, unsigned char* smem, int c0) {
   u64* s_kx = reinterpret_cast<u64*>(smem + L.kp_off);
   float* s_wk = reinterpret_cast<float*>(smem + L.wk_off);
   if (threadIdx.x < 3 * 8) {
@@ -216,7 +222,7 @@ __device__ __forceinline__ void pg_load_params(const AggArgs& a, const PgSmem& L
   }
   for (int e = threadIdx.x; e < kMaxKP * L.CpR; e += blockDim.x) {
     const int kp = e / L.CpR, c = e % L.CpR;
-    s_wk[e] = (kp < a.nkp && c < a.C) ? a.p1[(size_t)kp * a.C + c] : 0.f;
+    s_wk[e] = (kp < a.nkp && c0 + c < a.C) ? a.p1[(size_t)kp * a.C + c0 + c] : 0.f;
   }
 }
 
@@ -226,11 +232,16 @@ __device__ __forceinline__ void pg_load_params(const AggArgs& a, const PgSmem& L
 //   BWD = true : centre = support point j, neighbour rows = g_pm[q_e] over the transposed list of j;
 //                out[b,:,j] = acc ; d/dWk accumulated per warp in shared memory.            (persistent tiles)
 // =================================================================================================
-template <bool BWD>
+template <bool BWD, bool CHUNKED>
 __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const AggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const PgSmem L = pg_smem(a.Cp, BWD);
+  // CHUNKED = false (Cp <= 128, every BASELINE shape): one chunk, the constants below fold away
+  const int W = CHUNKED ? pg_chunk_width(a.Cp, gridDim.y) : a.Cp;
+  const int c0 = CHUNKED ? blockIdx.y * W : 0;     // this CTA's channel chunk
+  const int Cw = CHUNKED ? min(W, a.Cp - c0) : a.Cp;  // its (padded) width, a multiple of 4
+  const int Cv = CHUNKED ? min(Cw, a.C - c0) : a.C;   // real channels in it
+  const PgSmem L = pg_smem(W, BWD);
   const u64* s_kx = reinterpret_cast<const u64*>(smem + L.kp_off);
   const u64* s_ky = s_kx + 8;
   const u64* s_kz = s_kx + 16;
@@ -238,12 +249,12 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
   float2* s_ent = reinterpret_cast<float2*>(smem + L.ent_off) + (size_t)warp * 32 * kEntStride;
   float* s_out = reinterpret_cast<float*>(smem + L.out_off);
   float* s_aux = reinterpret_cast<float*>(smem + L.aux_off);
-  pg_load_params(a, L, smem);
+  pg_load_params(a, L, smem, c0);
   if constexpr (BWD)
     for (int e = threadIdx.x; e < kPgWarps * kMaxKP * L.CpR; e += blockDim.x) s_aux[e] = 0.f;
   __syncthreads();
 
-  const int G = L.CpR / 4;                  // lanes that own channels
+  const int G = CHUNKED ? Cw / 4 : L.CpR / 4;   // lanes that own channels
   const bool owner = lane < G;
   const int cl = owner ? lane * 4 : 0;      // the others shadow lane 0 (their results are dropped)
   const int row_bytes = L.CpR * (int)sizeof(float);
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int b = tile / tiles_per_cloud;
     const int p0 = (tile % tiles_per_cloud) * kPgTile;
-    const float* rows = (BWD ? a.g_pm : a.feat_pm) + (size_t)b * R * a.Cp + cl;
+    const float* rows = (BWD ? a.g_pm : a.feat_pm) + (size_t)b * R * a.Cp + c0 + cl;
     const float* cxyz = (BWD ? a.support_xyz : a.query_xyz) + (size_t)b * P * 3;   // centres
     const float* nxyz = (BWD ? a.query_xyz : a.support_xyz) + (size_t)b * R * 3;   // neighbours
     float4 bn1 = make_float4(0.f, 0.f, 0.f, 0.f), bn2 = bn1;                        // forward: sum, sum of squares
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
         const float cx = cxyz[p * 3 + 0], cy = cxyz[p * 3 + 1], cz = cxyz[p * 3 + 2];
         float4 fown = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (BWD)  // own features (d/dWk)
-          fown = __ldg(reinterpret_cast<const float4*>(a.feat_pm + ((size_t)b * a.N + p) * a.Cp + cl));
+          fown = __ldg(reinterpret_cast<const float4*>(a.feat_pm + ((size_t)b * a.N + p) * a.Cp + c0 + cl));
         for (int eb = e0; eb < e1; eb += 32) {
           const bool valid = eb + lane < e1;
           float dx = 0.f, dy = 0.f, dz = 0.f;
@@ -335,16 +346,16 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
     __syncthreads();
     // ---- tile -> channel-major (B,C,P)
     const int p = p0 + lane;
-    for (int c = warp; c < a.C; c += kPgWarps)
-      if (p < P) a.out[((size_t)b * a.C + c) * P + p] = s_out[(size_t)c * (kPgTile + 1) + lane];
+    for (int c = warp; c < Cv; c += kPgWarps)
+      if (p < P) a.out[((size_t)b * a.C + c0 + c) * P + p] = s_out[(size_t)c * (kPgTile + 1) + lane];
     if constexpr (!BWD) {
       if (a.partial) {  // BatchNorm partial sums of the tile: the warps' sums in a fixed order
-        for (int e = threadIdx.x; e < 2 * a.C; e += blockDim.x) {
-          const int s2 = e / a.C, c = e % a.C;
+        for (int e = threadIdx.x; e < 2 * Cv; e += blockDim.x) {
+          const int s2 = e / Cv, c = e % Cv;
           float t = 0.f;
 #pragma unroll
           for (int w = 0; w < kPgWarps; ++w) t += s_aux[((size_t)w * 2 + s2) * L.CpR + c];
-          a.partial[((size_t)tile * 2 + s2) * a.C + c] = t;
+          a.partial[((size_t)tile * 2 + s2) * a.C + c0 + c] = t;
         }
       }
     }
@@ -352,12 +363,15 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
   }
   if constexpr (BWD) {
     // ---- d/dWk: sum the warps' accumulators in a fixed order -> one partial row per CTA: (gridDim.x, nkp, C)
-    for (int e = threadIdx.x; e < a.nkp * a.C; e += blockDim.x) {
-      const int kp = e / a.C, c = e % a.C;
+    for (int e = threadIdx.x; e < a.nkp * Cv; e += blockDim.x) {
+      const int kp = e / Cv, c = e % Cv;
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < kPgWarps; ++w) t += s_aux[((size_t)w * kMaxKP + kp) * L.CpR + c];
-      a.partial[(size_t)blockIdx.x * a.nkp * a.C + e] = t;
+      if constexpr (CHUNKED)
+        a.partial[((size_t)blockIdx.x * a.nkp + kp) * a.C + c0 + c] = t;
+      else
+        a.partial[(size_t)blockIdx.x * a.nkp * a.C + e] = t;
     }
   }
 }
@@ -367,16 +381,23 @@ __global__ void __launch_bounds__(kPgWarps * 32, BWD ? 3 : 4) pg2_kernel(const A
 // ---------------------------------------------------------------------------------------------
 bool pg2_supported(const AggArgs& a) {
   if (getenv("CL3D_PG_V1")) return false;  // A/B switch: first-generation kernels (tests, profiling)
-  return a.Cp <= 128 && a.nkp >= 1 && a.nkp <= kMaxKP;  // Cp / 4 lanes own channels
+  return a.nkp >= 1 && a.nkp <= kMaxKP;
 }
 
 int pg2_launch_fwd(const AggArgs& a, cudaStream_t stream) {
   if (!pg2_supported(a)) return CL3D_ERR_UNSUPPORTED;
 
-  const PgSmem L = pg_smem(a.Cp, false);
+  const int nchunks = pg_num_chunks(a.Cp);
+  const PgSmem L = pg_smem(pg_chunk_width(a.Cp, nchunks), false);
   static std::atomic<unsigned long long> seen{0};
-  allow_big_smem(pg2_kernel<false>, seen);
-  pg2_kernel<false><<<a.ntiles, kPgWarps * 32, L.total, stream>>>(a);
+  if (nchunks == 1) {
+    allow_big_smem(pg2_kernel<false, false>, seen);
+    pg2_kernel<false, false><<<a.ntiles, kPgWarps * 32, L.total, stream>>>(a);
+  } else {
+    static std::atomic<unsigned long long> seen_c{0};
+    allow_big_smem(pg2_kernel<false, true>, seen_c);
+    pg2_kernel<false, true><<<dim3(a.ntiles, nchunks), kPgWarps * 32, L.total, stream>>>(a);
+  }
   CL3D_LAUNCHED(1);
   return check_launch("pg2_kernel<fwd>");
 }
@@ -384,10 +405,17 @@ int pg2_launch_fwd(const AggArgs& a, cudaStream_t stream) {
 int pg2_launch_bwd(const AggArgs& a, int grid_x, cudaStream_t stream) {
   if (!pg2_supported(a)) return CL3D_ERR_UNSUPPORTED;
 
-  const PgSmem L = pg_smem(a.Cp, true);
+  const int nchunks = pg_num_chunks(a.Cp);
+  const PgSmem L = pg_smem(pg_chunk_width(a.Cp, nchunks), true);
   static std::atomic<unsigned long long> seen{0};
-  allow_big_smem(pg2_kernel<true>, seen);
-  pg2_kernel<true><<<grid_x, kPgWarps * 32, L.total, stream>>>(a);
+  if (nchunks == 1) {
+    allow_big_smem(pg2_kernel<true, false>, seen);
+    pg2_kernel<true, false><<<grid_x, kPgWarps * 32, L.total, stream>>>(a);
+  } else {
+    static std::atomic<unsigned long long> seen_c{0};
+    allow_big_smem(pg2_kernel<true, true>, seen_c);
+    pg2_kernel<true, true><<<dim3(grid_x, nchunks), kPgWarps * 32, L.total, stream>>>(a);
+  }
   CL3D_LAUNCHED(1);
   return check_launch("pg2_kernel<bwd>");
 }
