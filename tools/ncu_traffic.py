@@ -9,7 +9,8 @@ from closerlook3d_b200.config import baseline_config
 MAP = [("gemm_tf32x3", "cl3d_sgemm_algo"), ("sgemm", "cl3d_sgemm_algo"), ("splitk_reduce", "cl3d_sgemm_algo"),
        ("ball_query", "cl3d_ball_query_csr"), ("grid_build_fused", "cl3d_ball_query_csr"), ("grid_params", "cl3d_ball_query_csr"),
        ("cell_", "cl3d_ball_query_csr"), ("zero_cells", "cl3d_ball_query_csr"), ("csr_", "cl3d_ball_query_csr"),
-       ("pg2_kernel<(bool)0", "cl3d_agg_fwd"), ("pg2_kernel<(bool)1", "cl3d_agg_bwd"), ("aggmax_fwd", "cl3d_agg_fwd"),
+       ("pg2_kernel<(bool)0", "cl3d_agg_fwd"), ("pg2_kernel<(bool)1", "cl3d_agg_bwd"), ("pg2_kernel<0", "cl3d_agg_fwd"),
+       ("pg2_kernel<1", "cl3d_agg_bwd"), ("aggmax_fwd", "cl3d_agg_fwd"),
        ("aggmax_bwd", "cl3d_agg_bwd"), ("nearest_query", "cl3d_nearest_query"),
        ("pwmlp_fwd_kernel", "cl3d_pwmlp_fwd_stats"), ("pwmlp_out", "cl3d_pwmlp_fwd_out"), ("pwmlp_bwd", "cl3d_pwmlp_bwd"),
        ("agg_fwd", "cl3d_agg_fwd"), ("sincos_fwd", "cl3d_agg_fwd"), ("agg_bwd", "cl3d_agg_bwd"), ("sincos_bwd", "cl3d_agg_bwd"),
@@ -29,8 +30,11 @@ for path in sys.argv[1:]:
     h = next(r for r in rows if r[0] == "ID")
     ki, mn, mu, mv = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Unit"), h.index("Metric Value")
     launches = collections.OrderedDict()   # id -> [name, bytes, us]
+    # a capture restricted to this library's kernels (capture_traffic.sh: -k regex:cl3d on mangled names) prints the
+    # names without the namespace; an unrestricted one is filtered here
+    namespaced = any("cl3d::" in r[ki] for r in rows if r[0] != "ID")
     for r in rows:
-        if r[0] == "ID" or "cl3d::" not in r[ki]:
+        if r[0] == "ID" or (namespaced and "cl3d::" not in r[ki]):
             continue
         e = launches.setdefault(r[0], [r[ki], 0.0, 0.0])
         v = float(r[mv].replace(",", "")) * SCALE.get(r[mu], 1)
