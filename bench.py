@@ -757,7 +757,9 @@ def main():
                 "algo_bytes_model": "SURVEY.md 8(d): (16C + 8K + 32) bytes/point x points per launch "
                                     f"= {step_algo_bytes_per_point(C, K)} x {pts_local}",
                 "kernel_time_ms": top["ms_per_call"], "peak_source": peak_src,
-                "share_of_step": top["ms_per_step"] / max(1e-9, sum(k["ms_per_step"] for k in kern)),
+                # share of the graph-replayed step (the entry points' own times sum to more than the step: the list
+                # build runs beside the forward on the side stream and its elapsed time includes waiting for SMs)
+                "share_of_step": top["ms_per_step"] / max(1e-9, res["ms_per_step"]),
                 "step_frac": step_bytes / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
                 "kernel_model_frac": (top["kernel_model_gbs"] / peak) if top.get("kernel_model_gbs") else None}
     cb = None
