@@ -50,6 +50,10 @@ def _ref_available():
     ("adaptive_weight", dict(adaptive_weight=dict(num_mlps=2, shared_channels=2, reduction="avg"))),
     ("pointwisemlp", dict(pointwisemlp=dict(feature_type="dp_fi_df", num_mlps=1, reduction="max"))),
     ("pseudo_grid", dict()),
+    # the max reductions the fused kernels of csrc/agg_max.cu are checked against
+    ("pospool", dict(pospool=dict(position_embedding="xyz", reduction="max"))),
+    ("pospool", dict(pospool=dict(position_embedding="sin_cos", reduction="max"))),
+    ("adaptive_weight", dict(adaptive_weight=dict(num_mlps=1, shared_channels=1, reduction="max"))),
 ])
 def test_oracle_matches_live_reference(oracle_ext, la_type, over):
     from oracle import la_oracle, ref_loader
